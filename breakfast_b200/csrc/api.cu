@@ -1,0 +1,792 @@
+// api.cu — host side of libbreakfast_b200.so: the C ABI declared in include/breakfast_b200.h.
+// Owns device memory, the stream, kernel launches and timers.  No torch, no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/breakfast_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at api.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+    g_err = buf;
+    (void)cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation) return BF_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return BF_ERR_NO_DEVICE;
+    return BF_ERR_CUDA;
+}
+
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__);   \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+#define TRY(expr)                    \
+    do {                             \
+        int rc_ = (expr);            \
+        if (rc_ != BF_OK) return rc_; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return BF_OK;
+        if (p) {
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, bytes);  // retry without slack
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return cuda_fail(e, "cudaMalloc", __LINE__);
+        }
+        cap = want;
+        return BF_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, ceil_div(n, block)); }
+
+}  // namespace
+
+struct bf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+
+    // options
+    int engine = BF_ENGINE_SKETCH;
+    int sketch_bits = 256;
+    int want_edges = 0;
+    int64_t cand_capacity = 0;  // 0 = auto
+    int blocks_per_sm = 0;      // 0 = occupancy
+
+    // problem
+    bool uploaded = false, ran = false, has_query = false;
+    int64_t n_rows = 0, n_query = 0, nnz = 0;
+    int32_t n_cols = 0;
+
+    // last run
+    int max_dist = 0, rank = 0, world = 1;
+    int K4 = 1, n_chunks = 1;
+    int64_t bits_per_row = 0, tilesA = 0, tilesB = 0;
+    unsigned long long cand_cap_used = 0;
+    float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
+
+    DevBuf indptr, indices, query_rows, is_query;
+    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts;
+    DevBuf bitsA, bitsB, jlo, wprefix, nwork, cand, edges, parent, labels, counters, scratch, scratch2;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_aux[2] = {};
+};
+
+namespace {
+
+using namespace bf;
+
+int set_device(bf_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return BF_OK;
+}
+
+// rows sorted by (clamped) cardinality: keys[0]/vals[0] hold the result (two ping-pong passes)
+int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2]) {
+    if (n == 0) return BF_OK;
+    const int nblocks = (int)ceil_div(n, SORT_ITEMS);
+    for (int i = 0; i < 2; ++i) {
+        TRY(keys[i].ensure(n * sizeof(uint32_t)));
+        TRY(vals[i].ensure(n * sizeof(int32_t)));
+    }
+    TRY(c->sort_counts.ensure((size_t)256 * nblocks * sizeof(uint32_t)));
+    k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(), rows_dev, n,
+                                                          keys[0].as<uint32_t>(), vals[0].as<int32_t>());
+    CKL();
+    for (int pass = 0; pass < 2; ++pass) {
+        const int in = pass & 1, out = in ^ 1, shift = 8 * pass;
+        k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
+                                                    c->sort_counts.as<uint32_t>(), nblocks);
+        CKL();
+        k_exclusive_scan<uint32_t><<<1, 1024, 0, c->stream>>>(c->sort_counts.as<uint32_t>(),
+                                                              (int64_t)256 * nblocks, nullptr);
+        CKL();
+        k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
+                                                       c->sort_counts.as<uint32_t>(), nblocks,
+                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>());
+        CKL();
+    }
+    return BF_OK;
+}
+
+int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
+    if (n == 0) return BF_OK;
+    const int64_t tiles = ceil_div(n, TILE);
+    const size_t bytes = (size_t)tiles * c->n_chunks * c->K4 * TILE * 16;
+    TRY(bits.ensure(bytes));
+    if (c->engine == BF_ENGINE_SKETCH) {
+        int log2m = 0;
+        while ((1 << log2m) < c->sketch_bits) ++log2m;
+        const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
+        k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
+                                                                 perm_dev, n, log2m, c->n_chunks, c->K4,
+                                                                 bits.as<uint32_t>());
+        CKL();
+    } else {
+        CK(cudaMemsetAsync(bits.p, 0, bytes, c->stream));
+        k_pack_full<<<grid_for(n * 32, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(),
+                                                                  c->indices.as<int32_t>(), perm_dev, n,
+                                                                  c->n_chunks, c->K4, bits.as<uint32_t>());
+        CKL();
+    }
+    return BF_OK;
+}
+
+template <int K4>
+int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int triangular) {
+    using L = PairSmem<K4>;
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device & 63]) {
+        CK(cudaFuncSetAttribute(k_pairs<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes));
+        attr_set[c->device & 63] = true;
+    }
+    int bps = c->blocks_per_sm;
+    if (bps <= 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pairs<K4>, PAIR_THREADS, L::kTotalBytes));
+        bps = std::max(1, std::min(bps, 4));
+    }
+    const unsigned grid = (unsigned)(c->num_sms * bps);
+    k_pairs<K4><<<grid, PAIR_THREADS, L::kTotalBytes, c->stream>>>(
+        A, B, c->n_chunks, nA, nB, c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(), c->tilesA,
+        c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank, c->world, c->cand.as<uint2>(),
+        c->cand_cap_used, c->counters.as<DevCounters>());
+    CKL();
+    return BF_OK;
+}
+
+int finish_labels(bf_ctx* c) {
+    const int64_t n = c->n_rows;
+    if (n == 0) return BF_OK;
+    k_uf_labels<<<grid_for(n, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n, c->labels.as<int32_t>());
+    CKL();
+    CK(cudaMemsetAsync(&c->counters.as<DevCounters>()->n_comp, 0, sizeof(unsigned int), c->stream));
+    k_count_roots<<<grid_for(n, 256), 256, 0, c->stream>>>(c->labels.as<int32_t>(), n,
+                                                           &c->counters.as<DevCounters>()->n_comp);
+    CKL();
+    return BF_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int bf_abi_version(void) { return BF_ABI_VERSION; }
+const char* bf_last_error(void) { return g_err.c_str(); }
+
+int bf_device_count(int* n_out) {
+    if (!n_out) return fail(BF_ERR_INVALID, "n_out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *n_out = 0;
+        return fail(BF_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    *n_out = n;
+    return BF_OK;
+}
+
+int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out) {
+    if (!ctx_out) return fail(BF_ERR_INVALID, "ctx_out is null");
+    *ctx_out = nullptr;
+    int n = 0;
+    TRY(bf_device_count(&n));
+    if (n <= 0) return fail(BF_ERR_NO_DEVICE, "no CUDA device visible; breakfast_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(BF_ERR_INVALID, "device index out of range");
+    bf_ctx* c = new (std::nothrow) bf_ctx();
+    if (!c) return fail(BF_ERR_OOM, "host allocation failed");
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess && prop.major < 9) {
+        delete c;
+        return fail(BF_ERR_NO_DEVICE, "device is older than sm_90: bulk-async copies/mbarrier unavailable (built for sm_100a)");
+    }
+    if (e == cudaSuccess) {
+        c->num_sms = prop.multiProcessorCount;
+        if (stream) {
+            c->stream = (cudaStream_t)stream;
+        } else {
+            e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+            c->own_stream = true;
+        }
+    }
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_aux[i]);
+    if (e == cudaSuccess) {
+        int rc = c->counters.ensure(sizeof(DevCounters));
+        if (rc == BF_OK) rc = c->nwork.ensure(sizeof(unsigned long long));
+        if (rc != BF_OK) {
+            bf_ctx_destroy(c);
+            return rc;
+        }
+    }
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "bf_ctx_create", __LINE__);
+        bf_ctx_destroy(c);
+        return rc;
+    }
+    *ctx_out = c;
+    return BF_OK;
+}
+
+void bf_ctx_destroy(bf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->indptr, &c->indices, &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
+                      &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
+                      &c->sort_counts, &c->bitsA, &c->bitsB, &c->jlo, &c->wprefix, &c->nwork, &c->cand,
+                      &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_aux) if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    (void)cudaGetLastError();
+    delete c;
+}
+
+int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return fail(BF_ERR_INVALID, "null argument");
+    std::string k(key);
+    if (k == "engine") {
+        if (value != BF_ENGINE_SKETCH && value != BF_ENGINE_FULL) return fail(BF_ERR_INVALID, "engine must be 0 (sketch) or 1 (full)");
+        c->engine = (int)value;
+    } else if (k == "sketch_bits") {
+        if (value < 128 || value > 2048 || (value & (value - 1))) return fail(BF_ERR_INVALID, "sketch_bits must be a power of two in [128, 2048]");
+        c->sketch_bits = (int)value;
+    } else if (k == "want_edges") {
+        c->want_edges = value ? 1 : 0;
+    } else if (k == "cand_capacity") {
+        if (value < 0) return fail(BF_ERR_INVALID, "cand_capacity must be >= 0");
+        c->cand_capacity = value;
+    } else if (k == "blocks_per_sm") {
+        if (value < 0 || value > 8) return fail(BF_ERR_INVALID, "blocks_per_sm must be in [0, 8]");
+        c->blocks_per_sm = (int)value;
+    } else {
+        return fail(BF_ERR_INVALID, "unknown option: " + k);
+    }
+    return BF_OK;
+}
+
+int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols,
+                  const int32_t* query_rows, int64_t n_query) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (n_rows < 0 || n_cols < 0 || n_rows > (int64_t)2147483647 - 2 * TILE) return fail(BF_ERR_INVALID, "n_rows/n_cols out of range");
+    if (n_rows > 0 && !indptr) return fail(BF_ERR_INVALID, "indptr is null");
+    if (query_rows == nullptr && n_query != 0 && n_query != n_rows) return fail(BF_ERR_INVALID, "n_query given without query_rows");
+    if (query_rows && (n_query < 0 || n_query > n_rows)) return fail(BF_ERR_INVALID, "n_query out of range");
+    int64_t nnz = 0;
+    if (n_rows > 0) {
+        if (indptr[0] != 0) return fail(BF_ERR_INVALID, "indptr[0] must be 0");
+        for (int64_t i = 0; i < n_rows; ++i)
+            if (indptr[i + 1] < indptr[i]) return fail(BF_ERR_INVALID, "indptr must be non-decreasing");
+        nnz = indptr[n_rows];
+        if (nnz > 0 && !indices) return fail(BF_ERR_INVALID, "indices is null");
+    }
+    if (query_rows) {
+        for (int64_t q = 0; q < n_query; ++q) {
+            if (query_rows[q] < 0 || query_rows[q] >= n_rows) return fail(BF_ERR_INVALID, "query row out of range");
+            if (q && query_rows[q] <= query_rows[q - 1]) return fail(BF_ERR_INVALID, "query_rows must be ascending and unique");
+        }
+    }
+    TRY(set_device(c));
+    c->uploaded = false;
+    c->ran = false;
+    CK(cudaEventRecord(c->ev_aux[0], c->stream));
+    TRY(c->indptr.ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
+    TRY(c->indices.ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    if (n_rows > 0) {
+        CK(cudaMemcpyAsync(c->indptr.p, indptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        if (nnz > 0) CK(cudaMemcpyAsync(c->indices.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        int64_t zero = 0;
+        CK(cudaMemcpyAsync(c->indptr.p, &zero, sizeof zero, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->has_query = query_rows != nullptr;
+    c->n_query = c->has_query ? n_query : n_rows;
+    if (c->has_query) {
+        TRY(c->query_rows.ensure((size_t)std::max<int64_t>(n_query, 1) * sizeof(int32_t)));
+        TRY(c->is_query.ensure((size_t)std::max<int64_t>(n_rows, 1)));
+        if (n_query > 0) CK(cudaMemcpyAsync(c->query_rows.p, query_rows, (size_t)n_query * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->is_query.p, 0, (size_t)std::max<int64_t>(n_rows, 1), c->stream));
+        if (n_query > 0) {
+            k_mark_rows<<<grid_for(n_query, 256), 256, 0, c->stream>>>(c->query_rows.as<int32_t>(), n_query, c->is_query.as<unsigned char>());
+            CKL();
+        }
+    }
+    CK(cudaEventRecord(c->ev_aux[1], c->stream));
+    // the caller's buffers may be pageable and are not retained: wait for the copies
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->ms_h2d, c->ev_aux[0], c->ev_aux[1]));
+    c->n_rows = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->uploaded = true;
+    return BF_OK;
+}
+
+int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->uploaded) return fail(BF_ERR_STATE, "bf_run before bf_upload_csr");
+    if (max_dist < 0) return fail(BF_ERR_INVALID, "max_dist must be >= 0");
+    if (world < 1 || rank < 0 || rank >= world) return fail(BF_ERR_INVALID, "need 0 <= rank < world");
+    TRY(set_device(c));
+    c->max_dist = max_dist;
+    c->rank = rank;
+    c->world = world;
+    c->ran = false;
+    c->ms_merge = 0;
+    const int64_t nB = c->n_rows, nA = c->n_query;
+
+    if (c->engine == BF_ENGINE_SKETCH) {
+        const int words = c->sketch_bits / 32;
+        c->K4 = std::min(4, words / 4);
+        c->n_chunks = words / (4 * c->K4);
+        c->bits_per_row = c->sketch_bits;
+    } else {
+        c->K4 = 4;
+        c->n_chunks = (int)std::max<int64_t>(1, ceil_div(c->n_cols, 512));
+        c->bits_per_row = (int64_t)c->n_chunks * 512;
+    }
+    c->tilesA = ceil_div(nA, TILE);
+    c->tilesB = ceil_div(nB, TILE);
+
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));
+    CK(cudaMemsetAsync(c->nwork.p, 0, sizeof(unsigned long long), c->stream));
+    TRY(c->parent.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int)));
+    TRY(c->labels.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int32_t)));
+    if (nB > 0) {
+        k_uf_init<<<grid_for(nB, 256), 256, 0, c->stream>>>(c->parent.as<int>(), nB);
+        CKL();
+    }
+
+    const bool active = nA > 0 && nB > 0;
+    DevBuf* keysA = c->has_query ? c->keysA : c->keysB;
+    DevBuf* valsA = c->has_query ? c->valsA : c->valsB;
+    if (active) {
+        // ---- K2: sort by cardinality
+        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB));
+        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA));
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    if (active) {
+        // ---- K1: bit-pack
+        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB));
+        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA));
+    }
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    if (active) {
+        // ---- K2b: schedule
+        TRY(c->jlo.ensure((size_t)c->tilesA * sizeof(int32_t)));
+        TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
+        k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
+            keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1,
+            c->jlo.as<int32_t>(), c->wprefix.as<unsigned long long>());
+        CKL();
+        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
+        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>());
+        CKL();
+        DevCounters* dc = c->counters.as<DevCounters>();
+        k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
+        CKL();
+        if (c->has_query) {
+            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, keysA[0].as<uint32_t>(), nA, max_dist, &dc->band_aa);
+            CKL();
+        }
+        // candidate buffer
+        unsigned long long cap = c->cand_capacity > 0 ? (unsigned long long)c->cand_capacity
+                                                      : (unsigned long long)std::max<int64_t>((int64_t)1 << 22, 8 * nB);
+        TRY(c->cand.ensure((size_t)cap * sizeof(uint2)));
+        c->cand_cap_used = cap;
+        if (c->want_edges) TRY(c->edges.ensure((size_t)cap * sizeof(uint2)));
+    }
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    if (active) {
+        // ---- K3: pairs
+        const uint4* A = (c->has_query ? c->bitsA : c->bitsB).as<uint4>();
+        const uint4* B = c->bitsB.as<uint4>();
+        const int tri = c->has_query ? 0 : 1;
+        if (c->K4 == 1) TRY(launch_pairs<1>(c, A, B, nA, nB, tri));
+        else if (c->K4 == 2) TRY(launch_pairs<2>(c, A, B, nA, nB, tri));
+        else TRY(launch_pairs<4>(c, A, B, nA, nB, tri));
+    }
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    if (active) {
+        // ---- K3b: verify + hook
+        k_verify_unite<<<c->num_sms * 8, 256, 0, c->stream>>>(
+            c->cand.as<uint2>(), c->cand_cap_used, valsA[0].as<int32_t>(), c->valsB[0].as<int32_t>(),
+            c->indptr.as<int64_t>(), c->indices.as<int32_t>(), max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
+            c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
+            c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
+        CKL();
+    }
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    // ---- K4: labels
+    TRY(finish_labels(c));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    c->ran = true;
+    return BF_OK;
+}
+
+int bf_labels_to_device(bf_ctx* c, void* dst_device) {
+    if (!c || !dst_device) return fail(BF_ERR_INVALID, "null argument");
+    if (!c->ran) return fail(BF_ERR_STATE, "no run to take labels from");
+    TRY(set_device(c));
+    if (c->n_rows > 0) CK(cudaMemcpyAsync(dst_device, c->labels.p, (size_t)c->n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    return BF_OK;
+}
+
+int bf_merge_labels_device(bf_ctx* c, const void* gathered_device, int32_t world) {
+    if (!c || !gathered_device) return fail(BF_ERR_INVALID, "null argument");
+    if (!c->ran) return fail(BF_ERR_STATE, "merge before run");
+    if (world < 1) return fail(BF_ERR_INVALID, "world must be >= 1");
+    TRY(set_device(c));
+    CK(cudaEventRecord(c->ev_aux[0], c->stream));
+    if (c->n_rows > 0) {
+        k_uf_merge_labels<<<grid_for(c->n_rows * world, 256), 256, 0, c->stream>>>(
+            c->parent.as<int>(), static_cast<const int32_t*>(gathered_device), c->n_rows, world);
+        CKL();
+    }
+    TRY(finish_labels(c));
+    CK(cudaEventRecord(c->ev_aux[1], c->stream));
+    c->ms_merge = -1.f;  // resolved in bf_sync
+    return BF_OK;
+}
+
+int bf_merge_labels_host(bf_ctx* c, const int32_t* gathered_host, int32_t world) {
+    if (!c || !gathered_host) return fail(BF_ERR_INVALID, "null argument");
+    if (!c->ran) return fail(BF_ERR_STATE, "merge before run");
+    if (world < 1) return fail(BF_ERR_INVALID, "world must be >= 1");
+    TRY(set_device(c));
+    const size_t bytes = (size_t)c->n_rows * world * sizeof(int32_t);
+    TRY(c->scratch.ensure(std::max<size_t>(bytes, 4)));
+    if (bytes) CK(cudaMemcpyAsync(c->scratch.p, gathered_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = bf_merge_labels_device(c, c->scratch.p, world);
+    if (rc != BF_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_union_lists(bf_ctx* c, const int64_t* list_indptr, const int32_t* list_members, int64_t n_lists) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->ran) return fail(BF_ERR_STATE, "bf_union_lists before run");
+    if (n_lists < 0) return fail(BF_ERR_INVALID, "n_lists < 0");
+    if (n_lists == 0) return BF_OK;
+    if (!list_indptr) return fail(BF_ERR_INVALID, "list_indptr is null");
+    const int64_t n_members = list_indptr[n_lists];
+    if (list_indptr[0] != 0 || n_members < 0) return fail(BF_ERR_INVALID, "bad list_indptr");
+    for (int64_t l = 0; l < n_lists; ++l)
+        if (list_indptr[l + 1] < list_indptr[l]) return fail(BF_ERR_INVALID, "list_indptr must be non-decreasing");
+    if (n_members == 0) return BF_OK;
+    if (!list_members) return fail(BF_ERR_INVALID, "list_members is null");
+    for (int64_t e = 0; e < n_members; ++e)
+        if (list_members[e] < 0 || list_members[e] >= c->n_rows) return fail(BF_ERR_INVALID, "list member out of range");
+    TRY(set_device(c));
+    TRY(c->scratch.ensure((size_t)(n_lists + 1) * sizeof(int64_t)));
+    TRY(c->scratch2.ensure((size_t)n_members * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(c->scratch.p, list_indptr, (size_t)(n_lists + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->scratch2.p, list_members, (size_t)n_members * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    k_uf_lists<<<grid_for(n_members, 256), 256, 0, c->stream>>>(c->parent.as<int>(), c->scratch.as<int64_t>(), c->scratch2.as<int32_t>(), n_lists, n_members);
+    CKL();
+    TRY(finish_labels(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_sync(bf_ctx* c, bf_stats* st) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->ran) return fail(BF_ERR_STATE, "bf_sync before bf_run");
+    TRY(set_device(c));
+    CK(cudaStreamSynchronize(c->stream));
+    DevCounters h;
+    unsigned long long nwork = 0;
+    CK(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&nwork, c->nwork.p, sizeof nwork, cudaMemcpyDeviceToHost));
+    const bool overflow = h.n_cand > c->cand_cap_used && c->n_query > 0 && c->n_rows > 0;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        const int64_t N = c->n_rows, Q = c->n_query;
+        st->n_rows = N;
+        st->n_query = Q;
+        st->n_cols = c->n_cols;
+        st->nnz = c->nnz;
+        st->bits_per_row = c->bits_per_row;
+        if (!c->has_query) {
+            st->pairs_total = N * (N - 1) / 2;
+            st->pairs_band = ((int64_t)h.band_ab - N) / 2;
+            st->tiles_total = c->tilesB * (c->tilesB + 1) / 2;
+        } else {
+            st->pairs_total = Q * N - Q - Q * (Q - 1) / 2;
+            st->pairs_band = (int64_t)h.band_ab - Q - ((int64_t)h.band_aa - Q) / 2;
+            st->tiles_total = c->tilesA * c->tilesB;
+        }
+        st->tiles_band = (int64_t)nwork;
+        st->tiles_rank = (int64_t)nwork > c->rank ? ((int64_t)nwork - c->rank + c->world - 1) / c->world : 0;
+        st->pairs_evaluated = st->tiles_rank * TILE * TILE;
+        st->n_candidates = (int64_t)h.n_cand;
+        st->n_edges = (int64_t)h.n_edges;
+        st->n_components = h.n_comp;
+        float ms = 0;
+        st->ms_h2d = c->ms_h2d;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); st->ms_sort = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); st->ms_pack = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); st->ms_sort += ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); st->ms_pairs = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); st->ms_verify = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); st->ms_cc = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6])); st->ms_total = ms;
+        if (c->ms_merge < 0) {
+            CK(cudaEventElapsedTime(&ms, c->ev_aux[0], c->ev_aux[1]));
+            st->ms_merge = ms;
+        }
+        st->ms_d2h = c->ms_d2h;
+    }
+    if (overflow) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "candidate buffer overflow: %llu candidates > capacity %llu; set cand_capacity and run again",
+                 (unsigned long long)h.n_cand, c->cand_cap_used);
+        return fail(BF_ERR_OVERFLOW, buf);
+    }
+    return BF_OK;
+}
+
+int bf_download_labels(bf_ctx* c, int32_t* labels_out) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->ran) return fail(BF_ERR_STATE, "no labels: run first");
+    if (c->n_rows == 0) return BF_OK;
+    if (!labels_out) return fail(BF_ERR_INVALID, "labels_out is null");
+    TRY(set_device(c));
+    CK(cudaEventRecord(c->ev_aux[0], c->stream));
+    CK(cudaMemcpyAsync(labels_out, c->labels.p, (size_t)c->n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev_aux[1], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->ms_d2h, c->ev_aux[0], c->ev_aux[1]));
+    return BF_OK;
+}
+
+int bf_edge_count(bf_ctx* c, int64_t* n_edges_out) {
+    if (!c || !n_edges_out) return fail(BF_ERR_INVALID, "null argument");
+    if (!c->ran) return fail(BF_ERR_STATE, "no run");
+    TRY(set_device(c));
+    CK(cudaStreamSynchronize(c->stream));
+    DevCounters h;
+    CK(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+    *n_edges_out = (int64_t)h.n_edges;
+    return BF_OK;
+}
+
+int bf_download_edges(bf_ctx* c, int32_t* src_out, int32_t* dst_out) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->ran || !c->want_edges) return fail(BF_ERR_STATE, "edges need option want_edges=1 before bf_run");
+    int64_t n = 0;
+    TRY(bf_edge_count(c, &n));
+    if (n == 0) return BF_OK;
+    if ((unsigned long long)n > c->cand_cap_used) return fail(BF_ERR_OVERFLOW, "edge buffer overflow");
+    if (!src_out || !dst_out) return fail(BF_ERR_INVALID, "null output");
+    std::vector<uint2> tmp((size_t)n);
+    CK(cudaMemcpy(tmp.data(), c->edges.p, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    // canonical order so the export is deterministic whatever the atomics did
+    std::sort(tmp.begin(), tmp.end(), [](const uint2& a, const uint2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    for (int64_t i = 0; i < n; ++i) {
+        src_out[i] = (int32_t)tmp[(size_t)i].x;
+        dst_out[i] = (int32_t)tmp[(size_t)i].y;
+    }
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot host-buffer API
+// ------------------------------------------------------------------------------------------------
+static int run_with_retry(bf_ctx* c, int32_t max_dist, bf_stats* st) {
+    bf_stats local;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        TRY(bf_run(c, max_dist, 0, 1));
+        int rc = bf_sync(c, &local);
+        if (rc == BF_ERR_OVERFLOW) {
+            c->cand_capacity = local.n_candidates + local.n_candidates / 4 + 1024;
+            continue;
+        }
+        if (rc != BF_OK) return rc;
+        if (st) *st = local;
+        return BF_OK;
+    }
+    return fail(BF_ERR_OVERFLOW, "candidate buffer overflow persisted after retries");
+}
+
+int bf_cluster_csr(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols, int32_t max_dist,
+                   int32_t device, int32_t engine, int32_t* labels_out, bf_stats* stats_out) {
+    bf_ctx* c = nullptr;
+    TRY(bf_ctx_create(device, nullptr, &c));
+    int rc = bf_ctx_set_option(c, "engine", engine);
+    if (rc == BF_OK) rc = bf_upload_csr(c, indptr, indices, n_rows, n_cols, nullptr, 0);
+    bf_stats st;
+    if (rc == BF_OK) rc = run_with_retry(c, max_dist, &st);
+    if (rc == BF_OK) rc = bf_download_labels(c, labels_out);
+    if (rc == BF_OK && stats_out) {
+        st.ms_d2h = c->ms_d2h;
+        *stats_out = st;
+    }
+    std::string keep = g_err;
+    bf_ctx_destroy(c);
+    g_err = keep;
+    return rc;
+}
+
+struct bf_edges_handle {
+    std::vector<int32_t> src, dst;
+};
+
+int bf_neighbours_csr(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols,
+                      const int32_t* query_rows, int64_t n_query, int32_t max_dist, int32_t device, int32_t engine,
+                      void** edges_handle_out, int64_t* n_edges_out, bf_stats* stats_out) {
+    if (!edges_handle_out || !n_edges_out) return fail(BF_ERR_INVALID, "null output");
+    *edges_handle_out = nullptr;
+    *n_edges_out = 0;
+    bf_ctx* c = nullptr;
+    TRY(bf_ctx_create(device, nullptr, &c));
+    int rc = bf_ctx_set_option(c, "engine", engine);
+    if (rc == BF_OK) rc = bf_ctx_set_option(c, "want_edges", 1);
+    if (rc == BF_OK) rc = bf_upload_csr(c, indptr, indices, n_rows, n_cols, query_rows, query_rows ? n_query : 0);
+    bf_stats st;
+    if (rc == BF_OK) rc = run_with_retry(c, max_dist, &st);
+    bf_edges_handle* h = nullptr;
+    if (rc == BF_OK) {
+        h = new (std::nothrow) bf_edges_handle();
+        if (!h) rc = fail(BF_ERR_OOM, "host allocation failed");
+    }
+    if (rc == BF_OK) {
+        try {
+            h->src.resize((size_t)st.n_edges);
+            h->dst.resize((size_t)st.n_edges);
+        } catch (...) {
+            rc = fail(BF_ERR_OOM, "host allocation failed");
+        }
+    }
+    if (rc == BF_OK) rc = bf_download_edges(c, h->src.data(), h->dst.data());
+    if (rc == BF_OK) {
+        *edges_handle_out = h;
+        *n_edges_out = st.n_edges;
+        if (stats_out) *stats_out = st;
+    } else {
+        delete h;
+    }
+    std::string keep = g_err;
+    bf_ctx_destroy(c);
+    g_err = keep;
+    return rc;
+}
+
+int bf_edges_copy(void* edges_handle, int32_t* src_out, int32_t* dst_out) {
+    if (!edges_handle) return fail(BF_ERR_INVALID, "null handle");
+    auto* h = static_cast<bf_edges_handle*>(edges_handle);
+    if (h->src.empty()) return BF_OK;
+    if (!src_out || !dst_out) return fail(BF_ERR_INVALID, "null output");
+    memcpy(src_out, h->src.data(), h->src.size() * sizeof(int32_t));
+    memcpy(dst_out, h->dst.data(), h->dst.size() * sizeof(int32_t));
+    return BF_OK;
+}
+
+void bf_edges_free(void* edges_handle) { delete static_cast<bf_edges_handle*>(edges_handle); }
+
+int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_t n_edges,
+                  const int64_t* list_indptr, const int32_t* list_members, int64_t n_lists, int32_t device,
+                  int32_t* labels_out, int64_t* n_components_out) {
+    if (n_rows < 0 || n_edges < 0 || n_lists < 0) return fail(BF_ERR_INVALID, "negative size");
+    if (n_edges > 0 && (!src || !dst)) return fail(BF_ERR_INVALID, "null edge arrays");
+    for (int64_t e = 0; e < n_edges; ++e)
+        if (src[e] < 0 || src[e] >= n_rows || dst[e] < 0 || dst[e] >= n_rows) return fail(BF_ERR_INVALID, "edge endpoint out of range");
+    bf_ctx* c = nullptr;
+    TRY(bf_ctx_create(device, nullptr, &c));
+    auto body = [&]() -> int {
+        c->n_rows = n_rows;
+        c->uploaded = true;
+        TRY(c->parent.ensure((size_t)std::max<int64_t>(n_rows, 1) * sizeof(int)));
+        TRY(c->labels.ensure((size_t)std::max<int64_t>(n_rows, 1) * sizeof(int32_t)));
+        CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));
+        if (n_rows > 0) {
+            k_uf_init<<<grid_for(n_rows, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n_rows);
+            CKL();
+        }
+        if (n_edges > 0) {
+            TRY(c->scratch.ensure((size_t)n_edges * sizeof(int32_t)));
+            TRY(c->scratch2.ensure((size_t)n_edges * sizeof(int32_t)));
+            CK(cudaMemcpyAsync(c->scratch.p, src, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->scratch2.p, dst, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            k_uf_edges<<<grid_for(n_edges, 256), 256, 0, c->stream>>>(c->parent.as<int>(), c->scratch.as<int32_t>(), c->scratch2.as<int32_t>(), n_edges);
+            CKL();
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        c->ran = true;
+        TRY(finish_labels(c));
+        TRY(bf_union_lists(c, list_indptr, list_members, n_lists));
+        TRY(bf_download_labels(c, labels_out));
+        if (n_components_out) {
+            DevCounters h;
+            CK(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+            *n_components_out = h.n_comp;
+        }
+        return BF_OK;
+    };
+    int rc = body();
+    std::string keep = g_err;
+    bf_ctx_destroy(c);
+    g_err = keep;
+    return rc;
+}
+
+int bf_pinned_alloc(int64_t bytes, void** ptr_out) {
+    if (!ptr_out || bytes < 0) return fail(BF_ERR_INVALID, "bad argument");
+    *ptr_out = nullptr;
+    CK(cudaHostAlloc(ptr_out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return BF_OK;
+}
+
+void bf_pinned_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

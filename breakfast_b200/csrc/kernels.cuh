@@ -1,0 +1,566 @@
+// kernels.cuh — sm_100a device code for the breakfast distance-and-clustering hot path.
+//
+// Pipeline (one pass = bf_run):
+//   K2  k_card_keys + 2x(k_sort_hist, k_scan, k_sort_scatter)   rows sorted by cardinality
+//                                                               (replaces the np.isclose band, breakfast.py:250-254)
+//   K1  k_pack_sketch / k_pack_full                              CSR -> tile-blocked bitsets
+//                                                               (replaces csr_matrix + row sums, breakfast.py:214,287)
+//   K2b k_schedule + k_scan                                      band-pruned tile-pair work list
+//   K3  k_pairs<K4>                                              tiled XOR/POPC + threshold + compaction
+//                                                               (replaces sklearn _sparse_manhattan + _reduce_func,
+//                                                                sklearn/metrics/_pairwise_fast.pyx:76-107, breakfast.py:226-228)
+//   K3b k_verify_unite                                           exact |A xor B| on CSR rows of the survivors + union
+//   K4  k_uf_* (hook / pointer-jump / labels)                    replaces _to_graph + networkx connected_components
+//                                                               (breakfast.py:93-113,325-326)
+//
+// Bitset layout in HBM ("tile-blocked"): rows are in cardinality-sorted order, grouped in tiles of
+// TILE=128 rows.  A row's bitset is cut into chunks of 4*K4 32-bit words (K4 = 16-byte groups per
+// chunk, K4 in {1,2,4}).  One (tile, chunk) block is contiguous:
+//       uint4 blk[K4][128]   blk[k4][row] = words 4*k4 .. 4*k4+3 of that row's chunk
+// so (a) a whole operand block is ONE 1-D bulk-async (TMA) copy into shared memory, and (b) the
+// 16 lanes that read 16 consecutive rows at the same k4 read 256 contiguous bytes: conflict-free
+// 128-bit shared loads.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bf {
+
+constexpr int TILE = 128;              // rows per tile (both operands)
+constexpr uint32_t KEY_CLAMP = 65535;  // cardinality sort key is clamped (1-Lipschitz, band test stays sound)
+constexpr int SORT_ITEMS = 1024;       // rows per block in the radix passes
+constexpr int PAIR_STAGES = 4;         // smem ring depth of the pair kernel
+constexpr int PAIR_CONSUMER_WARPS = 8;
+constexpr int PAIR_THREADS = (PAIR_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
+
+struct DevCounters {
+    unsigned long long n_cand;      // candidate cursor (may exceed capacity -> overflow)
+    unsigned long long n_edges;     // verified edges
+    unsigned long long band_ab;     // ordered in-band (a,b) count, A side vs B side (incl. self)
+    unsigned long long band_aa;     // ordered in-band (a,a') count inside the A side (rectangle runs)
+    unsigned int n_comp;
+    unsigned int pad;
+};
+
+// ------------------------------------------------------------------------------------------
+// K2: cardinality keys + stable LSD radix sort (2 x 8 bits) — deterministic permutation
+// ------------------------------------------------------------------------------------------
+__global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
+                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int32_t r = rows ? rows[q] : (int32_t)q;
+    int64_t c = indptr[r + 1] - indptr[r];
+    keys[q] = c > (int64_t)KEY_CLAMP ? KEY_CLAMP : (uint32_t)c;
+    vals[q] = r;
+}
+
+// counts[digit * nblocks + block] = number of rows of `block` whose digit == digit
+__global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
+                                                   uint32_t* __restrict__ counts, int nblocks) {
+    __shared__ uint16_t dig[SORT_ITEMS];
+    const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
+    const int m = (int)min((int64_t)SORT_ITEMS, n - base);
+    for (int i = threadIdx.x; i < m; i += 256) dig[i] = (uint16_t)((keys[base + i] >> shift) & 255u);
+    __syncthreads();
+    const uint16_t d = (uint16_t)threadIdx.x;
+    uint32_t c = 0;
+    for (int i = 0; i < m; ++i) c += (dig[i] == d);
+    counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = c;
+}
+
+// stable scatter: thread d walks the block's rows in order and places those with digit d
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys,
+                                                      const int32_t* __restrict__ vals, int64_t n, int shift,
+                                                      const uint32_t* __restrict__ offsets, int nblocks,
+                                                      uint32_t* __restrict__ keys_out,
+                                                      int32_t* __restrict__ vals_out) {
+    __shared__ uint32_t sk[SORT_ITEMS];
+    __shared__ int32_t sv[SORT_ITEMS];
+    const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
+    const int m = (int)min((int64_t)SORT_ITEMS, n - base);
+    for (int i = threadIdx.x; i < m; i += 256) {
+        sk[i] = keys[base + i];
+        sv[i] = vals[base + i];
+    }
+    __syncthreads();
+    const uint32_t d = threadIdx.x;
+    uint32_t pos = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    for (int i = 0; i < m; ++i) {
+        uint32_t k = sk[i];
+        if (((k >> shift) & 255u) == d) {
+            keys_out[pos] = k;
+            vals_out[pos] = sv[i];
+            ++pos;
+        }
+    }
+}
+
+// Single-block exclusive scan (in place), total written to *total_out (may be null).
+template <typename T>
+__global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, int64_t n, T* total_out) {
+    __shared__ T warp_sums[32];
+    __shared__ T carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        T v = i < n ? data[i] : (T)0;
+        T x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            T s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                T y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        T carry = carry_s;
+        T excl = carry + (warp ? warp_sums[warp - 1] : (T)0) + (x - v);
+        if (i < n) data[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: band-pruned tile schedule.  keys are sorted ascending, so tile min/max are its ends and the
+// B tiles that can hold an in-band partner of A tile I form one contiguous range [jlo, jlo+count).
+// ------------------------------------------------------------------------------------------
+__global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const uint32_t* __restrict__ keysB,
+                           int64_t nB, int max_dist, int triangular, int32_t* __restrict__ jlo,
+                           unsigned long long* __restrict__ count) {
+    const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
+    int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (I >= tA) return;
+    const uint32_t aMin = keysA[I * TILE];
+    const uint32_t aMax = keysA[min(nA, (I + 1) * TILE) - 1];
+    const uint32_t lo_t = aMin > (uint32_t)max_dist ? aMin - (uint32_t)max_dist : 0u;
+    const uint32_t hi_t = aMax + (uint32_t)max_dist;
+    // first J with bMax[J] >= lo_t
+    int64_t l = 0, r = tB;
+    while (l < r) {
+        int64_t mid = (l + r) >> 1;
+        uint32_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
+        if (bMax >= lo_t) r = mid; else l = mid + 1;
+    }
+    int64_t first = l;
+    // first J with bMin[J] > hi_t
+    l = 0; r = tB;
+    while (l < r) {
+        int64_t mid = (l + r) >> 1;
+        uint32_t bMin = keysB[mid * TILE];
+        if (bMin > hi_t) r = mid; else l = mid + 1;
+    }
+    int64_t end = l;
+    if (triangular && first < I) first = I;
+    jlo[I] = (int32_t)first;
+    count[I] = end > first ? (unsigned long long)(end - first) : 0ull;
+}
+
+// ordered in-band count: for every x in X, #{y in Y : |key_x - key_y| <= d}
+__global__ void __launch_bounds__(256) k_band_count(const uint32_t* __restrict__ keysX, int64_t nX,
+                                                    const uint32_t* __restrict__ keysY, int64_t nY, int max_dist,
+                                                    unsigned long long* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < nX) {
+        uint32_t k = keysX[i];
+        uint32_t lo_t = k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u;
+        uint32_t hi_t = k + (uint32_t)max_dist;
+        int64_t l = 0, r = nY;
+        while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] >= lo_t) r = m; else l = m + 1; }
+        int64_t a = l;
+        l = a; r = nY;
+        while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] > hi_t) r = m; else l = m + 1; }
+        c = (unsigned long long)(l - a);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += ws[w];
+        if (s) atomicAdd(out, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: bit-pack.  word `wd` of sorted row p lives at word_offset(...) (see layout above).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t word_offset(int64_t tile, int n_chunks, int K4, int wd, int row) {
+    const int wpc = 4 * K4;
+    const int chunk = wd / wpc, r = wd - chunk * wpc;
+    return ((((size_t)tile * n_chunks + chunk) * K4 + (r >> 2)) * TILE + row) * 4 + (r & 3);
+}
+
+__device__ __forceinline__ uint32_t fold_hash(uint32_t col, int log2m) {
+    return (col * 2654435761u) >> (32 - log2m);  // multiplicative hash -> [0, m)
+}
+
+// SKETCH: one block per tile; the folded tile is assembled in shared memory (XOR-toggle per feature)
+// and written out as one coalesced block.  HBM traffic: reads 4*nnz + 12*N bytes, writes N*m/8 bytes.
+__global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__ indptr,
+                                                     const int32_t* __restrict__ indices,
+                                                     const int32_t* __restrict__ perm, int64_t n, int log2m,
+                                                     int n_chunks, int K4, uint32_t* __restrict__ bits) {
+    extern __shared__ uint32_t tile_words[];  // n_chunks*K4*TILE*4 words
+    const int words_per_tile = n_chunks * K4 * TILE * 4;
+    for (int i = threadIdx.x; i < words_per_tile; i += 256) tile_words[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    for (int row = warp; row < TILE; row += 8) {
+        int64_t p = tile * TILE + row;
+        if (p >= n) break;
+        int32_t r = perm[p];
+        int64_t b = indptr[r], e = indptr[r + 1];
+        for (int64_t k = b + lane; k < e; k += 32) {
+            uint32_t h = fold_hash((uint32_t)indices[k], log2m);
+            atomicXor(&tile_words[word_offset(0, n_chunks, K4, (int)(h >> 5), row)], 1u << (h & 31));
+        }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)tile * words_per_tile);
+    const uint4* src = reinterpret_cast<const uint4*>(tile_words);
+    for (int i = threadIdx.x; i < words_per_tile / 4; i += 256) dst[i] = src[i];
+}
+
+// FULL: bit matrix pre-zeroed by the host (cudaMemsetAsync); one warp per row sets its bits.
+__global__ void __launch_bounds__(256) k_pack_full(const int64_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices,
+                                                   const int32_t* __restrict__ perm, int64_t n, int n_chunks,
+                                                   int K4, uint32_t* __restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= n) return;
+    int32_t r = perm[p];
+    int64_t b = indptr[r], e = indptr[r + 1];
+    const int64_t tile = p / TILE;
+    const int row = (int)(p - tile * TILE);
+    for (int64_t k = b + lane; k < e; k += 32) {
+        uint32_t c = (uint32_t)indices[k];
+        atomicOr(&bits[word_offset(tile, n_chunks, K4, (int)(c >> 5), row)], 1u << (c & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-async-copy (TMA, SASS UBLKCP) wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: tiled XOR/POPC pair kernel.
+//   persistent grid; work item = one band tile pair (I, J); item w of the global list belongs to
+//   rank (w % world); block b takes this rank's items b, b+grid, ...
+//   warp 8 = producer: one lane maps w -> (I,J) and issues two bulk-async copies per chunk into a
+//   4-stage shared-memory ring, completion on an mbarrier (expect_tx).
+//   warps 0-7 = consumers: thread (ty,tx) of a 16x16 grid owns the 8x8 pairs
+//   (ty+16i, tx+16j); per 16-byte k-group: 8 LDS.128 of B kept in registers, 8 LDS.128 of A, 256
+//   LOP3(xor)+POPC+IADD.  Threshold in the epilogue; the (rare) hits go to a global candidate list.
+//   Algorithmic work per evaluated pair: bits_per_row/32 POPC32 (+ as many XOR).
+// ------------------------------------------------------------------------------------------
+template <int K4>
+struct PairSmem {
+    static constexpr int kOperandBytes = K4 * TILE * 16;
+    static constexpr int kStageBytes = 2 * kOperandBytes;
+    static constexpr int kRingBytes = PAIR_STAGES * kStageBytes;
+    static constexpr int kTotalBytes = kRingBytes + PAIR_STAGES * (8 + 8 + 8);
+};
+
+template <int K4>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_chunks, int64_t nA, int64_t nB,
+        const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo, int64_t tilesA,
+        const unsigned long long* __restrict__ n_work, int threshold, int triangular, int rank, int world,
+        uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    using L = PairSmem<K4>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
+    uint64_t* empty_bar = full_bar + PAIR_STAGES;
+    int2* meta = reinterpret_cast<int2*>(empty_bar + PAIR_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PAIR_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const unsigned long long W = *n_work;
+    const unsigned long long first = (unsigned long long)rank + (unsigned long long)world * blockIdx.x;
+    const unsigned long long stride = (unsigned long long)world * gridDim.x;
+
+    if (warp == PAIR_CONSUMER_WARPS) {
+        // ------------------------------- producer -------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            int64_t I = 0;
+            for (unsigned long long w = first; w < W; w += stride) {
+                while (I + 1 < tilesA && __ldg(&wprefix[I + 1]) <= w) ++I;
+                const int J = __ldg(&jlo[I]) + (int)(w - __ldg(&wprefix[I]));
+                const uint4* gA = bitsA + (size_t)I * n_chunks * (K4 * TILE);
+                const uint4* gB = bitsB + (size_t)J * n_chunks * (K4 * TILE);
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    meta[stage] = make_int2((int)I, J);
+                    unsigned char* sa = smem + stage * L::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                    bulk_g2s(sa, gA + (size_t)c * (K4 * TILE), L::kOperandBytes, &full_bar[stage]);
+                    bulk_g2s(sa + L::kOperandBytes, gB + (size_t)c * (K4 * TILE), L::kOperandBytes,
+                             &full_bar[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // --------------------------------- consumers ---------------------------------
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    uint32_t it = 0;
+    for (unsigned long long w = first; w < W; w += stride) {
+        int acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+        int2 ij = make_int2(0, 0);
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+            const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+            mbar_wait(&full_bar[stage], ph);
+            const uint4* sA = reinterpret_cast<const uint4*>(smem + stage * L::kStageBytes);
+            const uint4* sB = sA + K4 * TILE;
+#pragma unroll
+            for (int k4 = 0; k4 < K4; ++k4) {
+                uint4 b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = sB[k4 * TILE + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 a = sA[k4 * TILE + ty + 16 * i];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc[i][j] += __popc(a.x ^ b[j].x) + __popc(a.y ^ b[j].y) + __popc(a.z ^ b[j].z) +
+                                     __popc(a.w ^ b[j].w);
+                    }
+                }
+            }
+            if (c == n_chunks - 1) ij = meta[stage];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
+        // epilogue: threshold. min-reduce first so the common case is ~1 op per pair.
+        int mn = acc[0][0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mn = min(mn, acc[i][j]);
+        if (mn <= threshold) {
+            const int64_t gi0 = (int64_t)ij.x * TILE + ty, gj0 = (int64_t)ij.y * TILE + tx;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (acc[i][j] <= threshold) {
+                        const int64_t gi = gi0 + 16 * i, gj = gj0 + 16 * j;
+                        if (gi < nA && gj < nB && (!triangular || gi < gj)) {
+                            unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
+                            if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
+                        }
+                    }
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: lock-free union-find (hook larger root under smaller root, path halving).  parent[v] <= v
+// always holds, so the final root of a component is its smallest row index — a canonical label
+// independent of edge order, rank count and scheduling.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* parent, int v) {
+    volatile int* P = parent;
+    int p = P[v];
+    while (p != v) {
+        int g = P[p];
+        if (g != p) P[v] = g;  // halving; g is an ancestor of v, so this never breaks the forest
+        v = p;
+        p = g;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+
+__global__ void k_uf_init(int* __restrict__ parent, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = (int)i;
+}
+
+__global__ void k_uf_labels(int* __restrict__ parent, int64_t n, int32_t* __restrict__ labels) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) labels[i] = uf_find(parent, (int)i);
+}
+
+__global__ void __launch_bounds__(256) k_count_roots(const int32_t* __restrict__ labels, int64_t n,
+                                                     unsigned int* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned int is_root = (i < n && labels[i] == (int32_t)i) ? 1u : 0u;
+    unsigned int m = __ballot_sync(0xffffffffu, is_root);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned int)__popc(m));
+}
+
+__global__ void k_uf_edges(int* __restrict__ parent, const int32_t* __restrict__ src,
+                           const int32_t* __restrict__ dst, int64_t n_edges) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < n_edges) uf_unite(parent, src[e], dst[e]);
+}
+
+// gathered[r][i] = label of row i on rank r  ->  union(i, gathered[r][i])
+__global__ void k_uf_merge_labels(int* __restrict__ parent, const int32_t* __restrict__ gathered, int64_t n,
+                                  int world) {
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * world) return;
+    int i = (int)(idx % n);
+    int l = gathered[idx];
+    if (l != i) uf_unite(parent, i, l);
+}
+
+// member lists (CSR): every member is united with the first member of its list
+__global__ void k_uf_lists(int* __restrict__ parent, const int64_t* __restrict__ list_indptr,
+                           const int32_t* __restrict__ members, int64_t n_lists, int64_t n_members) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n_members) return;
+    int64_t l = 0, r = n_lists;  // last list with indptr[l] <= e
+    while (l < r) {
+        int64_t m = (l + r) >> 1;
+        if (list_indptr[m + 1] <= e) l = m + 1; else r = m;
+    }
+    int head = members[list_indptr[l]];
+    int me = members[e];
+    if (me != head) uf_unite(parent, head, me);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: exact verification of the candidates on the CSR rows (two-pointer symmetric difference with
+// early exit at > max_dist — the same merge sklearn's _sparse_manhattan does, on integers) and hook.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
+               const int32_t* __restrict__ permB, const int64_t* __restrict__ indptr,
+               const int32_t* __restrict__ indices, int max_dist, int already_exact,
+               const unsigned char* __restrict__ is_query, int* __restrict__ parent, uint2* __restrict__ edges,
+               unsigned long long edge_cap, DevCounters* __restrict__ counters) {
+    const unsigned long long n = min(counters->n_cand, cand_cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp_id = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long base = warp_id * 32; base < n; base += n_warps * 32) {
+        const unsigned long long c = base + lane;
+        bool is_edge = false;
+        int ra = 0, rb = 0;
+        if (c < n) {
+            const uint2 pr = cand[c];
+            ra = permA[pr.x];
+            rb = permB[pr.y];
+            bool keep = true;
+            if (is_query) keep = (ra != rb) && !(is_query[rb] && ra > rb);
+            if (keep) {
+                int diff = 0;
+                if (!already_exact) {
+                    int64_t ia = indptr[ra], ea = indptr[ra + 1], ib = indptr[rb], eb = indptr[rb + 1];
+                    while (ia < ea && ib < eb) {
+                        int x = indices[ia], y = indices[ib];
+                        if (x == y) { ++ia; ++ib; }
+                        else {
+                            if (++diff > max_dist) break;
+                            if (x < y) ++ia; else ++ib;
+                        }
+                    }
+                    if (diff <= max_dist) {
+                        int64_t rest = (ea - ia) + (eb - ib);
+                        diff = rest > (int64_t)max_dist ? max_dist + 1 : diff + (int)rest;
+                    }
+                }
+                is_edge = diff <= max_dist;
+            }
+        }
+        if (is_edge) uf_unite(parent, ra, rb);
+        const unsigned int m = __ballot_sync(0xffffffffu, is_edge);
+        if (m) {
+            unsigned long long pos0 = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) pos0 = atomicAdd(&counters->n_edges, (unsigned long long)__popc(m));
+            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+            if (is_edge && edges) {
+                unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                if (pos < edge_cap) edges[pos] = make_uint2((uint32_t)min(ra, rb), (uint32_t)max(ra, rb));
+            }
+        }
+    }
+}
+
+__global__ void k_mark_rows(const int32_t* __restrict__ rows, int64_t n, unsigned char* __restrict__ flags) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[rows[i]] = 1;
+}
+
+}  // namespace bf

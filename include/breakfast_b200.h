@@ -1,0 +1,161 @@
+/*
+ * breakfast_b200.h — C ABI of libbreakfast_b200.so
+ *
+ * B200-native (sm_100a) replacement for the distance-and-clustering hot path of
+ * rki-mf1/breakfast.  The reference has no FFI of its own; the seam this ABI
+ * replaces is the Python call chain
+ *
+ *     breakfast.cluster_features                 src/breakfast/breakfast.py:279-340
+ *       -> sparse_feature_matrix row sums        src/breakfast/breakfast.py:285-291
+ *       -> get_neighbours_batch (per cardinality) src/breakfast/breakfast.py:223-276
+ *            -> sklearn pairwise_distances_chunked(metric="manhattan")
+ *               + _reduce_func (d <= max_dist)   src/breakfast/breakfast.py:226-228,261-267
+ *       -> _to_graph + connected_components      src/breakfast/breakfast.py:93-113,325-326
+ *
+ * Everything crossing this boundary is a plain pointer + size.  Host buffers are
+ * caller-owned, contiguous, never retained.  Every function returns BF_OK (0) or
+ * a negative bf_status; bf_last_error() gives the message for the calling
+ * thread.  No exceptions cross the boundary.  There is no CPU fallback: without
+ * a CUDA device every compute entry point fails with BF_ERR_NO_DEVICE.
+ *
+ * Row format: strictly binary CSR.  Row i owns indices[indptr[i]..indptr[i+1]),
+ * sorted ascending, unique, each in [0, n_cols).  Repeated tokens of one profile
+ * (reference: breakfast.py:210-212 appends them twice, sklearn then takes L1 on
+ * counts) are thermometer-coded into extra columns by the host before the call,
+ * so |A xor B| on these rows equals the reference's manhattan distance.
+ */
+#ifndef BREAKFAST_B200_H
+#define BREAKFAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_ABI_VERSION 1
+
+typedef enum bf_status {
+    BF_OK = 0,
+    BF_ERR_INVALID = -1,      /* bad argument / malformed CSR                         */
+    BF_ERR_NO_DEVICE = -2,    /* no usable CUDA device (there is no CPU fallback)     */
+    BF_ERR_CUDA = -3,         /* a CUDA runtime call failed; see bf_last_error()      */
+    BF_ERR_OOM = -4,          /* device or host allocation failed                     */
+    BF_ERR_OVERFLOW = -5,     /* candidate/edge buffer too small (async API only)     */
+    BF_ERR_STATE = -6         /* call order violated (e.g. run before upload)         */
+} bf_status;
+
+/* Engines for the pairwise phase (replaces sklearn _sparse_manhattan,
+ * sklearn/metrics/_pairwise_fast.pyx:34-107, as called at breakfast.py:261-267).
+ *   SKETCH: m-bit XOR-fold of every row (popc(fold(A)^fold(B)) <= |A xor B|, so
+ *           "> max_dist" rejects with no false negatives); the tiled XOR/POPC
+ *           kernel runs on the folded bitsets and survivors are verified exactly
+ *           on the CSR rows.  Exact.  Default.
+ *   FULL:   all n_cols columns as dense bitsets, tiled XOR/POPC over the whole
+ *           width, threshold is exact, no verify stage.  Exact.
+ */
+typedef enum bf_engine { BF_ENGINE_SKETCH = 0, BF_ENGINE_FULL = 1 } bf_engine;
+
+typedef struct bf_stats {
+    int64_t n_rows;           /* rows on the B side (all profiles)                     */
+    int64_t n_query;          /* rows on the A side (== n_rows for a full run)         */
+    int64_t n_cols;
+    int64_t nnz;
+    int64_t bits_per_row;     /* bitset width the pair kernel contracted over          */
+    int64_t pairs_total;      /* N(N-1)/2, or |Q|*|all| for a rectangle                */
+    int64_t pairs_band;       /* candidate pairs: ||A|-|B|| <= max_dist    */
+    int64_t pairs_evaluated;  /* pairs the tile kernel evaluated on this rank (incl. tile padding) */
+    int64_t tiles_total;      /* tile pairs of the whole (upper-triangular) tile space */
+    int64_t tiles_band;       /* tile pairs surviving cardinality-band pruning         */
+    int64_t tiles_rank;       /* of those, processed by this rank                      */
+    int64_t n_candidates;     /* sketch survivors handed to the exact verify kernel    */
+    int64_t n_edges;          /* verified edges (d <= max_dist), this rank             */
+    int64_t n_components;     /* after the last union-find/merge                       */
+    double ms_h2d, ms_sort, ms_pack, ms_pairs, ms_verify, ms_cc, ms_merge, ms_d2h, ms_total;
+} bf_stats;
+
+typedef struct bf_ctx bf_ctx;
+
+/* ---- library / device --------------------------------------------------- */
+int bf_abi_version(void);
+const char* bf_last_error(void);
+int bf_device_count(int* n_out);
+
+/* ---- context ------------------------------------------------------------ */
+/* `stream` is a cudaStream_t (or NULL: the context creates its own). All work of
+ * the context is enqueued on it, so a caller timing with events on that stream
+ * sees every kernel. */
+int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out);
+void bf_ctx_destroy(bf_ctx* ctx);
+/* Options: "engine" (bf_engine), "sketch_bits" (power of two, 128..4096),
+ * "want_edges" (0/1), "cand_capacity" (entries), "blocks_per_sm". */
+int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
+
+/* ---- async, device-resident API (used by bench.py and the multi-rank host) */
+/* H2D of the CSR (replaces the scipy csr_matrix construction, breakfast.py:214).
+ * `query_rows` (host, ascending, unique) selects the A side for the incremental
+ * path (reference: select_ind, breakfast.py:236-245,300); NULL = all rows. */
+int bf_upload_csr(bf_ctx* ctx, const int64_t* indptr, const int32_t* indices,
+                  int64_t n_rows, int32_t n_cols,
+                  const int32_t* query_rows, int64_t n_query);
+/* Enqueue one pass of the hot path on the uploaded rows for this rank's share of
+ * the band tiles: cardinality sort -> bit-pack -> tile schedule -> XOR/POPC pair
+ * kernel -> exact verify -> union-find -> labels (device).  Nothing is copied to
+ * the host; call bf_sync to wait and read counters.  world >= 1, 0 <= rank < world. */
+int bf_run(bf_ctx* ctx, int32_t max_dist, int32_t rank, int32_t world);
+/* D2D: copy this rank's labels (int32[n_rows], label = smallest row index of the
+ * row's component as seen by this rank) into caller device memory, e.g. a torch
+ * tensor that torch.distributed all-gathers over NCCL. */
+int bf_labels_to_device(bf_ctx* ctx, void* dst_device);
+/* Merge `world` gathered label arrays (device, int32[world][n_rows]) into the
+ * context's labels: union(i, labels_r[i]) for every r, then pointer jumping. */
+int bf_merge_labels_device(bf_ctx* ctx, const void* gathered_device, int32_t world);
+/* Same, but the gathered labels are on the host (single-process multi-GPU use). */
+int bf_merge_labels_host(bf_ctx* ctx, const int32_t* gathered_host, int32_t world);
+/* Extra hyper-edges: every list is a set of rows that must end up in one
+ * component (cached / ghost neighbour lists, reference cache.py:51-71 and
+ * breakfast.py:304,93-113).  CSR of lists on the host. Unions into current labels. */
+int bf_union_lists(bf_ctx* ctx, const int64_t* list_indptr, const int32_t* list_members,
+                   int64_t n_lists);
+/* Wait for the stream, read counters/timers; BF_ERR_OVERFLOW if the candidate
+ * buffer was too small (grow "cand_capacity" and run again). */
+int bf_sync(bf_ctx* ctx, bf_stats* stats_out);
+int bf_download_labels(bf_ctx* ctx, int32_t* labels_out /* [n_rows] */);
+/* Edge list of the last run (needs option want_edges=1): original row indices. */
+int bf_edge_count(bf_ctx* ctx, int64_t* n_edges_out);
+int bf_download_edges(bf_ctx* ctx, int32_t* src_out, int32_t* dst_out);
+
+/* ---- one-shot host-buffer API (what the Python host calls through ctypes) -- */
+/* Full run on one GPU: labels_out[i] = smallest row index in row i's component
+ * of the graph {d(a,b) <= max_dist}.  Replaces breakfast.py:314-318 + 325-326. */
+int bf_cluster_csr(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols,
+                   int32_t max_dist, int32_t device, int32_t engine,
+                   int32_t* labels_out, bf_stats* stats_out);
+/* Radius-neighbour edges between `query_rows` (NULL = all) and all rows; used for
+ * the cache export and the incremental path (breakfast.py:236-254: X = new rows,
+ * Y = all rows).  Each unordered pair is reported once. */
+int bf_neighbours_csr(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols,
+                      const int32_t* query_rows, int64_t n_query,
+                      int32_t max_dist, int32_t device, int32_t engine,
+                      void** edges_handle_out, int64_t* n_edges_out, bf_stats* stats_out);
+int bf_edges_copy(void* edges_handle, int32_t* src_out, int32_t* dst_out);
+void bf_edges_free(void* edges_handle);
+/* Connected components on the GPU over explicit edges plus member lists
+ * (either may be empty).  Replaces _to_graph + networkx connected_components,
+ * breakfast.py:93-113,325-326. */
+int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_t n_edges,
+                  const int64_t* list_indptr, const int32_t* list_members, int64_t n_lists,
+                  int32_t device, int32_t* labels_out, int64_t* n_components_out);
+
+/* ---- helpers --------------------------------------------------------------- */
+/* Page-locked host memory for callers that want DMA-speed H2D/D2H. */
+int bf_pinned_alloc(int64_t bytes, void** ptr_out);
+void bf_pinned_free(void* ptr);
+/* Register-resident pipe microbenchmarks on `device`; result in 1e9 lane-ops/s.
+ * name: "popc32", "lop3", "iadd3", "xor_popc_add". Roofline denominators. */
+int bf_measure_peak(int32_t device, const char* name, double* gops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREAKFAST_B200_H */
