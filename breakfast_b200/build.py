@@ -55,5 +55,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+SYNTH_SRC = CSRC / "synth.c"
+SYNTH_LIB = PKG_DIR / "libbfsynth.so"
+
+
+def build_synth(force: bool = False) -> Path:
+    """gcc build of the synthetic-profile generator (benchmark/test input only)."""
+    if not force and SYNTH_LIB.exists() and SYNTH_LIB.stat().st_mtime >= SYNTH_SRC.stat().st_mtime:
+        return SYNTH_LIB
+    gcc = shutil.which("gcc") or "gcc"
+    cmd = [gcc, "-O2", "-fPIC", "-shared", "-std=c11", str(SYNTH_SRC), "-o", str(SYNTH_LIB), "-lm"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return SYNTH_LIB
+
+
 if __name__ == "__main__":
+    build_synth(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

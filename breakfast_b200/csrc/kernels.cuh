@@ -18,8 +18,8 @@
 // chunk, K4 in {1,2,4}).  One (tile, chunk) block is contiguous:
 //       uint4 blk[K4][128]   blk[k4][row] = words 4*k4 .. 4*k4+3 of that row's chunk
 // so (a) a whole operand block is ONE 1-D bulk-async (TMA) copy into shared memory, and (b) the
-// 16 lanes that read 16 consecutive rows at the same k4 read 256 contiguous bytes: conflict-free
-// 128-bit shared loads.
+// 32 lanes of a warp that read 32 consecutive rows at the same k4 read 512 contiguous bytes:
+// conflict-free 128-bit shared loads.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -30,7 +30,7 @@ constexpr int TILE = 128;              // rows per tile (both operands)
 constexpr uint32_t KEY_CLAMP = 65535;  // cardinality sort key is clamped (1-Lipschitz, band test stays sound)
 constexpr int SORT_ITEMS = 1024;       // rows per block in the radix passes
 constexpr int PAIR_STAGES = 4;         // smem ring depth of the pair kernel
-constexpr int PAIR_CONSUMER_WARPS = 8;
+constexpr int PAIR_CONSUMER_WARPS = 16;
 constexpr int PAIR_THREADS = (PAIR_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 
 struct DevCounters {
@@ -299,10 +299,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // K3: tiled XOR/POPC pair kernel.
 //   persistent grid; work item = one band tile pair (I, J); item w of the global list belongs to
 //   rank (w % world); block b takes this rank's items b, b+grid, ...
-//   warp 8 = producer: one lane maps w -> (I,J) and issues two bulk-async copies per chunk into a
+//   warp 16 = producer: one lane maps w -> (I,J) and issues two bulk-async copies per chunk into a
 //   4-stage shared-memory ring, completion on an mbarrier (expect_tx).
-//   warps 0-7 = consumers: thread (ty,tx) of a 16x16 grid owns the 8x8 pairs
-//   (ty+16i, tx+16j); per 16-byte k-group: 8 LDS.128 of B kept in registers, 8 LDS.128 of A, 256
+//   warps 0-15 = consumers: thread (warp, lane) owns the 8x4 pairs (warp+16i, lane+32j); per
+//   16-byte k-group: 4 LDS.128 of B kept in registers, 8 broadcast LDS.128 of A, 128
 //   LOP3(xor)+POPC+IADD.  Threshold in the epilogue; the (rare) hits go to a global candidate list.
 //   Algorithmic work per evaluated pair: bits_per_row/32 POPC32 (+ as many XOR).
 // ------------------------------------------------------------------------------------------
@@ -342,38 +342,56 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
 
     if (warp == PAIR_CONSUMER_WARPS) {
         // ------------------------------- producer -------------------------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            int64_t I = 0;
-            for (unsigned long long w = first; w < W; w += stride) {
-                while (I + 1 < tilesA && __ldg(&wprefix[I + 1]) <= w) ++I;
-                const int J = __ldg(&jlo[I]) + (int)(w - __ldg(&wprefix[I]));
-                const uint4* gA = bitsA + (size_t)I * n_chunks * (K4 * TILE);
-                const uint4* gB = bitsB + (size_t)J * n_chunks * (K4 * TILE);
-                for (int c = 0; c < n_chunks; ++c, ++it) {
-                    const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
-                    mbar_wait(&empty_bar[stage], ph ^ 1u);
-                    meta[stage] = make_int2((int)I, J);
-                    unsigned char* sa = smem + stage * L::kStageBytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-                    bulk_g2s(sa, gA + (size_t)c * (K4 * TILE), L::kOperandBytes, &full_bar[stage]);
-                    bulk_g2s(sa + L::kOperandBytes, gB + (size_t)c * (K4 * TILE), L::kOperandBytes,
-                             &full_bar[stage]);
+        // All 32 lanes map one work item each to its tile pair (binary search on the work prefix:
+        // 32 independent chains of L2 loads in flight), then lane 0 issues the copies item by item.
+        uint32_t it = 0;
+        for (unsigned long long k0 = 0;; k0 += 32) {
+            const unsigned long long w = first + (k0 + lane) * stride;
+            if (first + k0 * stride >= W) break;
+            int I = 0, J = 0;
+            if (w < W) {
+                int64_t lo = 0, hi = tilesA - 1;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi + 1) >> 1;
+                    if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
                 }
+                I = (int)lo;
+                J = __ldg(&jlo[I]) + (int)(w - __ldg(&wprefix[I]));
+            }
+            for (int l = 0; l < 32; ++l) {
+                if (first + (k0 + l) * stride >= W) break;
+                const int Il = __shfl_sync(0xffffffffu, I, l), Jl = __shfl_sync(0xffffffffu, J, l);
+                if (lane == 0) {
+                    const uint4* gA = bitsA + (size_t)Il * n_chunks * (K4 * TILE);
+                    const uint4* gB = bitsB + (size_t)Jl * n_chunks * (K4 * TILE);
+                    for (int c = 0; c < n_chunks; ++c, ++it) {
+                        const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+                        mbar_wait(&empty_bar[stage], ph ^ 1u);
+                        meta[stage] = make_int2(Il, Jl);
+                        unsigned char* sa = smem + stage * L::kStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                        bulk_g2s(sa, gA + (size_t)c * (K4 * TILE), L::kOperandBytes, &full_bar[stage]);
+                        bulk_g2s(sa + L::kOperandBytes, gB + (size_t)c * (K4 * TILE), L::kOperandBytes,
+                                 &full_bar[stage]);
+                    }
+                }
+                __syncwarp();
             }
         }
         return;
     }
 
     // --------------------------------- consumers ---------------------------------
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // 16 warps; thread (ty = warp, tx = lane) owns the 8 x 4 pairs (ty + 16 i, tx + 32 j).  A rows are
+    // warp-uniform (broadcast LDS.128), B rows are 32 consecutive 16-byte groups (conflict-free).
+    const int tx = lane, ty = warp;
     uint32_t it = 0;
     for (unsigned long long w = first; w < W; w += stride) {
-        int acc[8][8];
+        int acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0;
         int2 ij = make_int2(0, 0);
         for (int c = 0; c < n_chunks; ++c, ++it) {
             const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
@@ -382,14 +400,14 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
             const uint4* sB = sA + K4 * TILE;
 #pragma unroll
             for (int k4 = 0; k4 < K4; ++k4) {
-                uint4 b[8];
+                uint4 b[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = sB[k4 * TILE + tx + 16 * j];
+                for (int j = 0; j < 4; ++j) b[j] = sB[k4 * TILE + tx + 32 * j];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint4 a = sA[k4 * TILE + ty + 16 * i];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         acc[i][j] += __popc(a.x ^ b[j].x) + __popc(a.y ^ b[j].y) + __popc(a.z ^ b[j].z) +
                                      __popc(a.w ^ b[j].w);
                     }
@@ -399,26 +417,31 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
         }
-        // epilogue: threshold. min-reduce first so the common case is ~1 op per pair.
+        // epilogue: threshold.  3-input min tree first (~0.5 op per pair); only a thread that owns a
+        // hit builds a hit mask (straight-line, no branches) and walks its set bits, so the emit code
+        // exists once and the instruction footprint of the hot loop stays small (an unrolled
+        // per-accumulator branch here cost 38 % stall_no_inst in the first ncu capture).
         int mn = acc[0][0];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mn = min(mn, acc[i][j]);
+            for (int j = 0; j < 4; ++j) mn = min(mn, acc[i][j]);
         if (mn <= threshold) {
-            const int64_t gi0 = (int64_t)ij.x * TILE + ty, gj0 = (int64_t)ij.y * TILE + tx;
+            uint32_t mask = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (acc[i][j] <= threshold) {
-                        const int64_t gi = gi0 + 16 * i, gj = gj0 + 16 * j;
-                        if (gi < nA && gj < nB && (!triangular || gi < gj)) {
-                            unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
-                            if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) mask |= (acc[i][j] <= threshold ? 1u : 0u) << (i * 4 + j);
+            const int64_t gi0 = (int64_t)ij.x * TILE + ty, gj0 = (int64_t)ij.y * TILE + tx;
+            while (mask) {
+                const int bit = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const int64_t gi = gi0 + 16 * (bit >> 2), gj = gj0 + 32 * (bit & 3);
+                if (gi < nA && gj < nB && (!triangular || gi < gj)) {
+                    unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
+                    if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
                 }
+            }
         }
     }
 }
