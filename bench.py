@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — candidate pairs/s of the breakfast distance-and-clustering hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (BASELINE.json metric): 1,000,000 unique synthetic SARS-CoV-2 profiles (seed 1), --max-dist 1,
+strictly binary CSR of the filtered profiles.  One step = one pass of the hot path on that batch:
+cardinality sort -> bit-pack -> band tile schedule -> tiled XOR/POPC pair kernel -> exact verify ->
+union-find -> labels (N > 1: the band tile pairs are dealt cyclically to the ranks, then the labels are
+all-gathered over NCCL and re-united on every rank).  `value` = candidate pairs (||A|-|B|| <= max_dist,
+SURVEY 8d) per second with the CSR already resident in HBM; `e2e` = the same through the C ABI with
+pinned HOST buffers (H2D of the CSR and D2H of the labels inside the timed region, every step).
+
+The line also carries `roofline` (the pair kernel against the POPC pipe peak measured in this run) and
+`cpu_baseline` (the oracle port — the reference's per-cardinality scikit-learn path — on a bounded sample
+of the same workload, on this box's host cores).  `--impl reference` times only that CPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_PROFILES = 1_000_000
+SEED = 1
+MAX_DIST = 1
+CPU_SAMPLE = 16_000          # profiles in the bounded CPU sample (about 10-20 s of scikit-learn work)
+METRIC = "candidate_pairs_per_s"
+UNIT = "pairs/s"
+WORKLOAD = f"synthetic {N_PROFILES} unique SARS-CoV-2 covsonar_dna profiles (seed {SEED}), --max-dist {MAX_DIST}"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def pairs_band_of(card, max_dist):
+    import numpy as np
+    h = np.bincount(card).astype(object)
+    total = sum(int(c) * (int(c) - 1) // 2 for c in h)
+    for k in range(1, max_dist + 1):
+        total += sum(int(h[c]) * int(h[c + k]) for c in range(len(h) - k))
+    return int(total)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (scikit-learn pairwise_distances_chunked per cardinality)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_setup(n_sample):
+    import numpy as np
+    from scipy.sparse import csr_matrix
+    from breakfast_b200 import synth
+    prof = synth.generate(N_PROFILES, seed=SEED)
+    indptr, indices, n_cols = prof.csr()
+    ip = indptr[: n_sample + 1]
+    ix = indices[: ip[-1]]
+    X = csr_matrix((np.ones(ix.size, dtype=np.int64), ix.astype(np.int64), ip), shape=(n_sample, n_cols))
+    band = pairs_band_of(np.diff(ip), MAX_DIST)
+    return X, band
+
+
+def cpu_step(X):
+    from oracle import ref_port
+    stats = {}
+    t0 = time.perf_counter()
+    lists = ref_port.neighbour_lists(X, MAX_DIST, stats=stats)
+    n_links = sum(len(l) for l in lists)
+    return time.perf_counter() - t0, stats.get("evaluations", 0), n_links
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # before scikit-learn is imported (console.py:150)
+    X, band = cpu_sample_setup(CPU_SAMPLE)
+    for _ in range(args.warmup):
+        cpu_step(X)
+    times, evals = [], 0
+    for _ in range(args.steps):
+        t, evals, _ = cpu_step(X)
+        times.append(t)
+    total = sum(times)
+    value = band * args.steps / total
+    sample = (f"first {CPU_SAMPLE} profiles of the workload per step: {band} candidate pairs, {evals} ordered "
+              f"distance evaluations by the reference's per-cardinality batches")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "max_dist": MAX_DIST, "sample_profiles": CPU_SAMPLE},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
+    ap.add_argument("--engine", default="sketch", choices=["sketch", "full"])
+    ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    from breakfast_b200 import _native, synth
+    from breakfast_b200.dist import RankRunner
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            log(f"--gpus {args.gpus} needs one process per GPU: launch with python -m torch.distributed.run "
+                f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 ... bench.py --gpus {args.gpus}")
+            return 2
+        args.gpus = world
+    _native.require_device()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.profiles
+    t0 = time.time()
+    prof = synth.generate(n, seed=SEED)
+    indptr, indices, n_cols = prof.csr()
+    del prof
+    if rank == 0:
+        log(f"[bench] generated {n} profiles, nnz={indices.size}, n_cols={n_cols} in {time.time() - t0:.1f}s")
+
+    # pinned host copies (the e2e leg copies from these every step)
+    lib = _native.load()
+    p_indptr, p_indices = C.c_void_p(), C.c_void_p()
+    assert lib.bf_pinned_alloc(indptr.nbytes, C.byref(p_indptr)) == 0
+    assert lib.bf_pinned_alloc(indices.nbytes, C.byref(p_indices)) == 0
+    C.memmove(p_indptr, indptr.ctypes.data, indptr.nbytes)
+    C.memmove(p_indices, indices.ctypes.data, indices.nbytes)
+    labels_host = np.empty(n, dtype=np.int32)
+    p_labels = C.c_void_p()
+    assert lib.bf_pinned_alloc(labels_host.nbytes, C.byref(p_labels)) == 0
+
+    peaks = {name: _native.measure_peak(name, local_rank) for name in ("popc32", "lop3")}  # also warms the clocks
+
+    # a real (non-default) torch stream: the library enqueues on it, torch events and NCCL order against it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits)
+    ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
+    runner = RankRunner(ctx, n, rank, world)
+
+    # ---- device-resident leg: `value`
+    for _ in range(args.warmup):
+        runner.step(MAX_DIST)
+    st = ctx.sync()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        runner.step(MAX_DIST)
+    ev1.record()
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    st = ctx.sync()      # counters + per-launch sums over the timed steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = st.pairs_band / (ms_per_step * 1e-3)
+
+    # per-launch duration of the dominant kernel over the timed region (CUDA events on the launching stream)
+    runs = max(1, min(st.runs_since_sync, 128))
+    ms_pairs = st.ms_pairs_sum / runs
+    popc_per_launch = st.pairs_evaluated * (st.bits_per_row // 32)
+    achieved = popc_per_launch / (ms_pairs * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(f"k_pairs_{args.engine}_{st.bits_per_row}_n{n}_w{world}")
+        except Exception:
+            traffic = None
+    launches = st.kernel_launches
+
+    # ---- end-to-end leg through the host-buffer C ABI: H2D CSR + pass + D2H labels, every step
+    def e2e_step():
+        ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
+        runner.step(MAX_DIST)
+        _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    st_e2e = ctx.sync()
+    C.memmove(labels_host.ctypes.data, p_labels, labels_host.nbytes)
+    ok = bool((labels_host <= np.arange(n)).all() and np.array_equal(labels_host[labels_host], labels_host))
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            os.environ["OMP_NUM_THREADS"] = str(cores)
+            import numpy as _np
+            from scipy.sparse import csr_matrix
+            ns = min(CPU_SAMPLE, n)
+            ip = indptr[: ns + 1]
+            ix = indices[: ip[-1]]
+            X = csr_matrix((_np.ones(ix.size, dtype=_np.int64), ix.astype(_np.int64), ip), shape=(ns, n_cols))
+            band = pairs_band_of(_np.diff(ip), MAX_DIST)
+            sec, evals, _ = cpu_step(X)
+            cpu = {"value": band / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {ns} profiles of the workload: {band} candidate pairs, {evals} ordered distance "
+                             f"evaluations (reference batches through scikit-learn), {sec:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n == N_PROFILES else f"{n} profiles (override)", "max_dist": MAX_DIST,
+                       "engine": args.engine, "bits_per_row": st.bits_per_row, "n_cols": n_cols, "nnz": int(indices.size),
+                       "candidate_pairs": st.pairs_band, "pairs_total": st.pairs_total, "tiles_band": st.tiles_band,
+                       "edges": None if world > 1 else st.n_edges, "components": st.n_components,
+                       "l2_policy": "inputs larger than L2 (CSR 360 MB + per-step rebuilt bitsets); no explicit flush",
+                       "parallelism": f"tile-partition x{world}" if world > 1 else "single GPU"},
+            "clocks": clock_info,
+            "e2e": {"value": st.pairs_band / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(indptr.nbytes + indices.nbytes), "d2h_bytes_per_step": int(labels_host.nbytes),
+                    "labels_sane": ok},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": f"k_pairs<K4> ({args.engine}, {st.bits_per_row} bits/row)", "bound": "int_pipe_popc",
+                         "achieved": achieved, "peak": peaks["popc32"], "unit": "GPOPC32/s", "frac": achieved / peaks["popc32"],
+                         "traffic": traffic, "ms_per_launch": ms_pairs, "popc32_per_launch": int(popc_per_launch),
+                         "peak_source": "bf_measure_peak('popc32') measured in this process; MEASURED_PEAKS.json holds only "
+                                        "HBM and bf16 peaks and this kernel is bound by the POPC (XU) pipe",
+                         "kernel_share_of_step": ms_pairs / (st.ms_total_sum / runs) if st.ms_total_sum else None},
+            "cpu_baseline": cpu,
+            "phases_ms": {k: getattr(st, k) for k in ("ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge")},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    for p in (p_indptr, p_indices, p_labels):
+        lib.bf_pinned_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

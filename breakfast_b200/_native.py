@@ -37,7 +37,9 @@ class Stats(C.Structure):
                    "n_components")
     _dbl_fields = ("ms_h2d", "ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge", "ms_d2h",
                    "ms_total")
-    _fields_ = [(n, C.c_int64) for n in _int_fields] + [(n, C.c_double) for n in _dbl_fields]
+    _fields_ = ([(n, C.c_int64) for n in _int_fields] + [(n, C.c_double) for n in _dbl_fields]
+                + [("runs_since_sync", C.c_int64), ("kernel_launches", C.c_int64),
+                   ("ms_pairs_sum", C.c_double), ("ms_total_sum", C.c_double)])
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -35,6 +35,7 @@ int cuda_fail(cudaError_t e, const char* what, int line) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__);   \
     } while (0)
 #define CKL() CK(cudaGetLastError())
+#define CKLC(c) do { CK(cudaGetLastError()); ++(c)->launches_since_sync; } while (0)
 #define TRY(expr)                    \
     do {                             \
         int rc_ = (expr);            \
@@ -109,6 +110,11 @@ struct bf_ctx {
     DevBuf bitsA, bitsB, jlo, wprefix, nwork, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
+    // per-run event ring so that bf_sync can report sums over all runs since the last sync
+    static constexpr int kRing = 128;
+    cudaEvent_t ring[kRing][4] = {};  // pass start, pairs start, pairs end, pass end
+    int64_t runs_since_sync = 0;
+    int64_t launches_since_sync = 0;
 };
 
 namespace {
@@ -131,19 +137,19 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
     TRY(c->sort_counts.ensure((size_t)256 * nblocks * sizeof(uint32_t)));
     k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(), rows_dev, n,
                                                           keys[0].as<uint32_t>(), vals[0].as<int32_t>());
-    CKL();
+    CKLC(c);
     for (int pass = 0; pass < 2; ++pass) {
         const int in = pass & 1, out = in ^ 1, shift = 8 * pass;
         k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
                                                     c->sort_counts.as<uint32_t>(), nblocks);
-        CKL();
+        CKLC(c);
         k_exclusive_scan<uint32_t><<<1, 1024, 0, c->stream>>>(c->sort_counts.as<uint32_t>(),
                                                               (int64_t)256 * nblocks, nullptr);
-        CKL();
+        CKLC(c);
         k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
                                                        c->sort_counts.as<uint32_t>(), nblocks,
                                                        keys[out].as<uint32_t>(), vals[out].as<int32_t>());
-        CKL();
+        CKLC(c);
     }
     return BF_OK;
 }
@@ -160,13 +166,13 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
         k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
                                                                  perm_dev, n, log2m, c->n_chunks, c->K4,
                                                                  bits.as<uint32_t>());
-        CKL();
+        CKLC(c);
     } else {
         CK(cudaMemsetAsync(bits.p, 0, bytes, c->stream));
         k_pack_full<<<grid_for(n * 32, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(),
                                                                   c->indices.as<int32_t>(), perm_dev, n,
                                                                   c->n_chunks, c->K4, bits.as<uint32_t>());
-        CKL();
+        CKLC(c);
     }
     return BF_OK;
 }
@@ -189,7 +195,7 @@ int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t 
         A, B, c->n_chunks, nA, nB, c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(), c->tilesA,
         c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank, c->world, c->cand.as<uint2>(),
         c->cand_cap_used, c->counters.as<DevCounters>());
-    CKL();
+    CKLC(c);
     return BF_OK;
 }
 
@@ -197,11 +203,11 @@ int finish_labels(bf_ctx* c) {
     const int64_t n = c->n_rows;
     if (n == 0) return BF_OK;
     k_uf_labels<<<grid_for(n, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n, c->labels.as<int32_t>());
-    CKL();
+    CKLC(c);
     CK(cudaMemsetAsync(&c->counters.as<DevCounters>()->n_comp, 0, sizeof(unsigned int), c->stream));
     k_count_roots<<<grid_for(n, 256), 256, 0, c->stream>>>(c->labels.as<int32_t>(), n,
                                                            &c->counters.as<DevCounters>()->n_comp);
-    CKL();
+    CKLC(c);
     return BF_OK;
 }
 
@@ -254,6 +260,8 @@ int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out) {
     }
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_aux[i]);
+    for (int i = 0; i < bf_ctx::kRing && e == cudaSuccess; ++i)
+        for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&c->ring[i][j]);
     if (e == cudaSuccess) {
         int rc = c->counters.ensure(sizeof(DevCounters));
         if (rc == BF_OK) rc = c->nwork.ensure(sizeof(unsigned long long));
@@ -282,6 +290,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_aux) if (e) cudaEventDestroy(e);
+    for (auto& r : c->ring) for (auto& e : r) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -354,7 +363,7 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
         CK(cudaMemsetAsync(c->is_query.p, 0, (size_t)std::max<int64_t>(n_rows, 1), c->stream));
         if (n_query > 0) {
             k_mark_rows<<<grid_for(n_query, 256), 256, 0, c->stream>>>(c->query_rows.as<int32_t>(), n_query, c->is_query.as<unsigned char>());
-            CKL();
+            CKLC(c);
         }
     }
     CK(cudaEventRecord(c->ev_aux[1], c->stream));
@@ -394,14 +403,16 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     c->tilesA = ceil_div(nA, TILE);
     c->tilesB = ceil_div(nB, TILE);
 
+    cudaEvent_t* ring = c->ring[c->runs_since_sync % bf_ctx::kRing];
     CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(cudaEventRecord(ring[0], c->stream));
     CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));
     CK(cudaMemsetAsync(c->nwork.p, 0, sizeof(unsigned long long), c->stream));
     TRY(c->parent.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int)));
     TRY(c->labels.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int32_t)));
     if (nB > 0) {
         k_uf_init<<<grid_for(nB, 256), 256, 0, c->stream>>>(c->parent.as<int>(), nB);
-        CKL();
+        CKLC(c);
     }
 
     const bool active = nA > 0 && nB > 0;
@@ -426,16 +437,16 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
             keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1,
             c->jlo.as<int32_t>(), c->wprefix.as<unsigned long long>());
-        CKL();
+        CKLC(c);
         CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
         k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>());
-        CKL();
+        CKLC(c);
         DevCounters* dc = c->counters.as<DevCounters>();
         k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
-        CKL();
+        CKLC(c);
         if (c->has_query) {
             k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, keysA[0].as<uint32_t>(), nA, max_dist, &dc->band_aa);
-            CKL();
+            CKLC(c);
         }
         // candidate buffer
         unsigned long long cap = c->cand_capacity > 0 ? (unsigned long long)c->cand_capacity
@@ -445,6 +456,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         if (c->want_edges) TRY(c->edges.ensure((size_t)cap * sizeof(uint2)));
     }
     CK(cudaEventRecord(c->ev[3], c->stream));
+    CK(cudaEventRecord(ring[1], c->stream));
     if (active) {
         // ---- K3: pairs
         const uint4* A = (c->has_query ? c->bitsA : c->bitsB).as<uint4>();
@@ -455,6 +467,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         else TRY(launch_pairs<4>(c, A, B, nA, nB, tri));
     }
     CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaEventRecord(ring[2], c->stream));
     if (active) {
         // ---- K3b: verify + hook
         k_verify_unite<<<c->num_sms * 8, 256, 0, c->stream>>>(
@@ -462,12 +475,14 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             c->indptr.as<int64_t>(), c->indices.as<int32_t>(), max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
             c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
             c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
-        CKL();
+        CKLC(c);
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
     // ---- K4: labels
     TRY(finish_labels(c));
     CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(cudaEventRecord(ring[3], c->stream));
+    ++c->runs_since_sync;
     c->ran = true;
     return BF_OK;
 }
@@ -489,7 +504,7 @@ int bf_merge_labels_device(bf_ctx* c, const void* gathered_device, int32_t world
     if (c->n_rows > 0) {
         k_uf_merge_labels<<<grid_for(c->n_rows * world, 256), 256, 0, c->stream>>>(
             c->parent.as<int>(), static_cast<const int32_t*>(gathered_device), c->n_rows, world);
-        CKL();
+        CKLC(c);
     }
     TRY(finish_labels(c));
     CK(cudaEventRecord(c->ev_aux[1], c->stream));
@@ -531,7 +546,7 @@ int bf_union_lists(bf_ctx* c, const int64_t* list_indptr, const int32_t* list_me
     CK(cudaMemcpyAsync(c->scratch.p, list_indptr, (size_t)(n_lists + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->scratch2.p, list_members, (size_t)n_members * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     k_uf_lists<<<grid_for(n_members, 256), 256, 0, c->stream>>>(c->parent.as<int>(), c->scratch.as<int64_t>(), c->scratch2.as<int32_t>(), n_lists, n_members);
-    CKL();
+    CKLC(c);
     TRY(finish_labels(c));
     CK(cudaStreamSynchronize(c->stream));
     return BF_OK;
@@ -584,7 +599,17 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
             st->ms_merge = ms;
         }
         st->ms_d2h = c->ms_d2h;
+        st->runs_since_sync = c->runs_since_sync;
+        st->kernel_launches = c->launches_since_sync;
+        const int64_t covered = std::min<int64_t>(c->runs_since_sync, bf_ctx::kRing);
+        for (int64_t k = 0; k < covered; ++k) {
+            cudaEvent_t* r = c->ring[(c->runs_since_sync - 1 - k) % bf_ctx::kRing];
+            CK(cudaEventElapsedTime(&ms, r[1], r[2])); st->ms_pairs_sum += ms;
+            CK(cudaEventElapsedTime(&ms, r[0], r[3])); st->ms_total_sum += ms;
+        }
     }
+    c->runs_since_sync = 0;
+    c->launches_since_sync = 0;
     if (overflow) {
         char buf[256];
         snprintf(buf, sizeof buf, "candidate buffer overflow: %llu candidates > capacity %llu; set cand_capacity and run again",
@@ -749,7 +774,7 @@ int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_
         CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));
         if (n_rows > 0) {
             k_uf_init<<<grid_for(n_rows, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n_rows);
-            CKL();
+            CKLC(c);
         }
         if (n_edges > 0) {
             TRY(c->scratch.ensure((size_t)n_edges * sizeof(int32_t)));
@@ -757,7 +782,7 @@ int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_
             CK(cudaMemcpyAsync(c->scratch.p, src, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(c->scratch2.p, dst, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
             k_uf_edges<<<grid_for(n_edges, 256), 256, 0, c->stream>>>(c->parent.as<int>(), c->scratch.as<int32_t>(), c->scratch2.as<int32_t>(), n_edges);
-            CKL();
+            CKLC(c);
             CK(cudaStreamSynchronize(c->stream));
         }
         c->ran = true;

@@ -1,0 +1,144 @@
+"""Host-side glue between the reference-shaped Python interface and the native CUDA library.
+
+Nothing in here computes distances or components: it tokenises profiles into a strictly binary CSR
+(thermometer-coding repeated tokens so that set symmetric difference equals the reference's L1
+distance on token counts, breakfast.py:210-212 + sklearn manhattan) and hands it to
+libbreakfast_b200.so.  If the library or the GPU is missing the calls raise — there is no fallback.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native
+
+
+def default_device() -> int:
+    return int(os.environ.get("BREAKFAST_B200_DEVICE", "0"))
+
+
+def default_engine() -> str:
+    return os.environ.get("BREAKFAST_B200_ENGINE", "sketch")
+
+
+def _context_options() -> dict:
+    opts = {}
+    if "BREAKFAST_B200_SKETCH_BITS" in os.environ:
+        opts["sketch_bits"] = int(os.environ["BREAKFAST_B200_SKETCH_BITS"])
+    return opts
+
+
+def tokenise(features, sep: str):
+    """Token ids per profile, vocabulary by first appearance, duplicates kept, empty tokens skipped —
+    exactly the traversal of reference sparse_feature_matrix (breakfast.py:199-213).
+
+    Returns (indptr int64 [n+1], indices int64 [n_tokens], vocabulary dict token -> id).
+    """
+    vocab: dict = {}
+    lookup = vocab.setdefault
+    flat: list = []
+    extend = flat.extend
+    ends = np.empty(len(features) + 1, dtype=np.int64)
+    ends[0] = 0
+    for r, text in enumerate(features):
+        if not isinstance(text, float) and text:  # NaN profiles and "" have no tokens
+            extend([lookup(tok, len(vocab)) for tok in text.split(sep) if tok])
+        ends[r + 1] = len(flat)
+    return ends, np.asarray(flat, dtype=np.int64), vocab
+
+
+def thermometer_binarise(indptr: np.ndarray, indices: np.ndarray, n_vocab: int):
+    """Binary CSR with sorted unique int32 columns whose set distance equals L1 on token counts.
+
+    The k-th repeat (k >= 1) of token t inside one profile becomes the extra feature (t, k); then
+    |A xor B| = sum_t |count_A(t) - count_B(t)|, which is what the reference computes because scipy
+    sums duplicate CSR entries before sklearn's manhattan kernel sees them.
+    """
+    n = len(indptr) - 1
+    if indices.size == 0:
+        return indptr.astype(np.int64), np.zeros(0, np.int32), int(n_vocab)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    order = np.lexsort((indices, rows))
+    rows_s, cols_s = rows[order], indices[order]
+    same = np.zeros(cols_s.size, dtype=bool)
+    same[1:] = (rows_s[1:] == rows_s[:-1]) & (cols_s[1:] == cols_s[:-1])
+    if not same.any():
+        return indptr.astype(np.int64), cols_s.astype(np.int32), int(n_vocab)
+    # rank of every entry inside its run of equal (row, col)
+    run_start = np.flatnonzero(~same)
+    run_id = np.cumsum(~same) - 1
+    rank = np.arange(cols_s.size) - run_start[run_id]
+    extra = rank > 0
+    keys = cols_s[extra] * (rank.max() + 1) + rank[extra]
+    uniq, inv = np.unique(keys, return_inverse=True)
+    cols_b = cols_s.copy()
+    cols_b[extra] = n_vocab + inv
+    order2 = np.lexsort((cols_b, rows_s))
+    return indptr.astype(np.int64), cols_b[order2].astype(np.int32), int(n_vocab + uniq.size)
+
+
+def binary_csr(features, sep: str):
+    indptr, indices, vocab = tokenise(features, sep)
+    return thermometer_binarise(indptr, indices, len(vocab))
+
+
+@dataclass
+class ClusterResult:
+    labels: np.ndarray                       # int32 [n]: smallest row index of the row's component
+    stats: dict = field(default_factory=dict)
+    edges: tuple | None = None               # (src, dst) int32, src < dst, when requested
+
+
+def components_full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None) -> ClusterResult:
+    """All-pairs run on one GPU: radius-neighbour graph at max_dist + connected components."""
+    device = default_device() if device is None else device
+    engine = default_engine() if engine is None else engine
+    _native.require_device()
+    with _native.Context(device=device, engine=engine, want_edges=int(bool(want_edges)), **_context_options()) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(max_dist)
+        labels = ctx.download_labels()
+        edges = ctx.download_edges() if want_edges else None
+    return ClusterResult(labels, st.as_dict(), edges)
+
+
+def components_incremental(indptr, indices, n_cols, max_dist, new_rows, list_indptr, list_members,
+                           want_edges=False, device=None, engine=None) -> ClusterResult:
+    """Incremental run: only the new x all block is evaluated (reference: X = new rows, Y = all rows,
+    breakfast.py:236-254) and the cached neighbour lists are united on top (breakfast.py:304)."""
+    device = default_device() if device is None else device
+    engine = default_engine() if engine is None else engine
+    _native.require_device()
+    new_rows = np.unique(np.asarray(new_rows, dtype=np.int32))
+    with _native.Context(device=device, engine=engine, want_edges=int(bool(want_edges)), **_context_options()) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols, query_rows=new_rows)
+        st = ctx.run_sync(max_dist)
+        if len(list_indptr) > 1:
+            ctx.union_lists(list_indptr, list_members)
+            st = ctx.sync()
+        labels = ctx.download_labels()
+        edges = ctx.download_edges() if want_edges else None
+    return ClusterResult(labels, st.as_dict(), edges)
+
+
+def adjacency_lists(n_rows: int, rows, src, dst):
+    """Neighbour lists in the shape the reference caches them (list of ascending int64 arrays, each
+    containing the query row itself, breakfast.py:226-228,274-275): one full list per row of
+    sorted(unique(rows))."""
+    rows = np.unique(np.asarray(rows, dtype=np.int64))
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    a = np.concatenate([src, dst, rows])
+    b = np.concatenate([dst, src, rows])
+    wanted = np.zeros(n_rows, dtype=bool)
+    wanted[rows] = True
+    keep = wanted[a]
+    a, b = a[keep], b[keep]
+    order = np.lexsort((b, a))
+    a, b = a[order], b[order]
+    counts = np.bincount(a, minlength=n_rows)[rows]
+    starts = np.concatenate(([0], np.cumsum(counts)))
+    # `rows` is ascending (np.unique), so the groups come out in the same order
+    return [b[starts[i]:starts[i + 1]] for i in range(len(rows))]

@@ -82,8 +82,11 @@ class SynthProfiles:
             csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
             indptr = csum[indptr]
             codes = codes[keep]
-        uniq, inv = np.unique(codes, return_inverse=True)
-        return np.ascontiguousarray(indptr, dtype=np.int64), inv.astype(np.int32), int(len(uniq))
+        # dense column ids in ascending code order (a lookup table beats np.unique at 10^8 entries)
+        present = np.zeros(int(codes.max()) + 1 if codes.size else 1, dtype=bool)
+        present[codes] = True
+        col_of = np.cumsum(present, dtype=np.int32) - 1
+        return np.ascontiguousarray(indptr, dtype=np.int64), col_of[codes], int(present.sum())
 
     def features(self, var_type: str = "covsonar_dna", sep: str = " ") -> list:
         uniq, inv = np.unique(self.codes, return_inverse=True)

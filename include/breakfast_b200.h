@@ -72,6 +72,11 @@ typedef struct bf_stats {
     int64_t n_edges;          /* verified edges (d <= max_dist), this rank             */
     int64_t n_components;     /* after the last union-find/merge                       */
     double ms_h2d, ms_sort, ms_pack, ms_pairs, ms_verify, ms_cc, ms_merge, ms_d2h, ms_total;
+    /* accumulated over every bf_run since the previous bf_sync (at most the last 256 runs): */
+    int64_t runs_since_sync;  /* how many bf_run calls these sums cover                        */
+    int64_t kernel_launches;  /* kernels this library launched in those runs (incl. merges)    */
+    double ms_pairs_sum;      /* summed device time of the pair kernel (CUDA events, own stream) */
+    double ms_total_sum;      /* summed device time of whole passes                            */
 } bf_stats;
 
 typedef struct bf_ctx bf_ctx;

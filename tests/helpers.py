@@ -1,0 +1,122 @@
+"""Shared helpers for the parity tests: golden manifest, CLI runner, oracle stand-ins."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+_FLAGS = {"id_col": "--id-col", "clust_col": "--clust-col", "var_type": "--var-type", "sep2": "--sep2",
+          "max_dist": "--max-dist", "min_cluster_size": "--min-cluster-size", "trim_start": "--trim-start",
+          "trim_end": "--trim-end", "reference_length": "--reference-length", "sep": "--sep"}
+
+
+def load_manifest() -> dict:
+    return json.loads((GOLDEN / "manifest.json").read_text())
+
+
+def cases(kind=None):
+    out = []
+    for c in load_manifest()["cases"]:
+        is_chain = "chain" in c
+        needs_cache = is_chain or "cache_from" in c or "reference_cache_file" in c
+        k = "chain" if is_chain else ("cached" if needs_cache else "plain")
+        if kind is None or k == kind:
+            out.append(c)
+    return out
+
+
+def cli_args(opts: dict) -> list:
+    a = []
+    for k, v in opts.items():
+        if k in _FLAGS:
+            a += [_FLAGS[k], str(v)]
+        elif k == "skip_del":
+            a.append("--skip-del" if v else "--no-skip-del")
+        elif k == "skip_ins":
+            a.append("--skip-ins" if v else "--no-skip-ins")
+        else:
+            raise KeyError(k)
+    return a
+
+
+def run_cli(input_rel: str, opts: dict, outdir: Path, cache_in=None, cache_out=None) -> str:
+    """Run the product CLI (breakfast_b200.console.main) like the reference's tests do."""
+    import click.testing
+    from breakfast_b200 import console
+    args = ["--input-file", str(GOLDEN / input_rel), "--outdir", str(outdir)] + cli_args(opts)
+    if cache_in:
+        args += ["--input-cache", str(cache_in)]
+    if cache_out:
+        args += ["--output-cache", str(cache_out)]
+    res = click.testing.CliRunner().invoke(console.main, args)
+    if res.exit_code != 0:
+        raise AssertionError(f"CLI failed ({res.exit_code}) for {args}:\n{res.output}\n{res.exception!r}")
+    return (outdir / "clusters.tsv").read_text()
+
+
+def assert_matches(case: dict, expected_rel: str, got_text: str):
+    want_path = GOLDEN / expected_rel
+    if case.get("compare") == "table":
+        # the reference's own goldens are compared the way its tests compare them
+        from io import StringIO
+        assert pd.read_table(want_path, sep="\t").equals(pd.read_table(StringIO(got_text), sep="\t")), case["name"]
+    else:
+        assert got_text == want_path.read_text(), f"{case['name']}: clusters.tsv differs from {expected_rel}"
+
+
+def canonical_labels(labels: np.ndarray) -> np.ndarray:
+    """relabel components by their smallest member (labels may be any partition ids)."""
+    labels = np.asarray(labels)
+    n = labels.size
+    mins = {}
+    for i, l in enumerate(labels.tolist()):
+        if l not in mins:
+            mins[l] = i
+    return np.array([mins[l] for l in labels.tolist()], dtype=np.int32) if n else np.zeros(0, np.int32)
+
+
+def merge_labels_cpu(gathered: np.ndarray) -> np.ndarray:
+    """Semantics of the multi-rank label merge, on the CPU, for checking: union(i, gathered[r][i])."""
+    import oracle
+    world, n = gathered.shape
+    src = np.tile(np.arange(n, dtype=np.int32), world)
+    dst = np.ascontiguousarray(gathered, dtype=np.int32).ravel()
+    return oracle.components(n, src, dst)
+
+
+class OracleEngine:
+    """Stand-in for breakfast_b200.engine.components_* backed by the CPU oracle.  CPU tests use it to
+    exercise the host pipeline (parsing, dedup, cache re-indexing, labelling, output) without a GPU.
+    Test infrastructure only: installed with monkeypatch, never reachable from the product."""
+
+    @staticmethod
+    def full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None):
+        import oracle
+        from breakfast_b200.engine import ClusterResult
+        src, dst = oracle.edges(indptr, indices, max_dist)
+        labels = oracle.components(len(indptr) - 1, src, dst)
+        return ClusterResult(labels, {}, (src, dst) if want_edges else None)
+
+    @staticmethod
+    def incremental(indptr, indices, n_cols, max_dist, new_rows, list_indptr, list_members, want_edges=False,
+                    device=None, engine=None):
+        import oracle
+        from breakfast_b200.engine import ClusterResult
+        new_rows = np.unique(np.asarray(new_rows, dtype=np.int32))
+        n = len(indptr) - 1
+        if new_rows.size:
+            src, dst = oracle.edges(indptr, indices, max_dist, queries=new_rows)
+        else:
+            src = dst = np.zeros(0, np.int32)
+        labels = oracle.components(n, src, dst, list_indptr, list_members)
+        return ClusterResult(labels, {}, (src, dst) if want_edges else None)
+
+    @classmethod
+    def install(cls, monkeypatch):
+        from breakfast_b200 import engine
+        monkeypatch.setattr(engine, "components_full", cls.full)
+        monkeypatch.setattr(engine, "components_incremental", cls.incremental)

@@ -1,0 +1,319 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (and through the CLI on top of it),
+against the CPU oracle and the committed golden files.  Bit-exact — the work is integer/indexing.
+Run on the B200 box:  python -m pytest tests -m gpu
+"""
+import ctypes as C
+import shutil
+
+import numpy as np
+import pytest
+
+import oracle
+from breakfast_b200 import _native, synth
+from tests import helpers
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["sketch", "full"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    _native.require_device()  # fail loudly (do not skip): the GPU suite must run on the GPU
+
+
+def rows_to_csr(rows, n_cols=None):
+    indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate([np.asarray(sorted(r), dtype=np.int32) for r in rows]) if indptr[-1] else np.zeros(0, np.int32)
+    if n_cols is None:
+        n_cols = int(indices.max()) + 1 if indices.size else 1
+    return indptr, indices.astype(np.int32), n_cols
+
+
+def edge_set(src, dst):
+    return set(zip(np.asarray(src).tolist(), np.asarray(dst).tolist()))
+
+
+# ------------------------------------------------------------------ goldens through the CLI
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", helpers.cases("plain"), ids=lambda c: c["name"])
+def test_cli_goldens(case, engine, tmp_path, monkeypatch):
+    monkeypatch.setenv("BREAKFAST_B200_ENGINE", engine)
+    helpers.assert_matches(case, case["expected"], helpers.run_cli(case["input"], case["opts"], tmp_path))
+
+
+@pytest.mark.parametrize("case", [c for c in helpers.cases("cached") if "cache_from" in c], ids=lambda c: c["name"])
+def test_cli_cached_goldens(case, tmp_path):
+    first = case["cache_from"]
+    cache = tmp_path / "cachedir" / "cache.pkl"
+    helpers.run_cli(first["input"], first["opts"], tmp_path / "first", cache_out=cache)
+    helpers.assert_matches(case, case["expected"],
+                           helpers.run_cli(case["input"], case["opts"], tmp_path / "second", cache_in=cache))
+
+
+@pytest.mark.parametrize("case", [c for c in helpers.cases("cached") if "reference_cache_file" in c],
+                         ids=lambda c: c["name"])
+def test_cli_reference_written_cache(case, tmp_path):
+    cache = tmp_path / "ref.cache"
+    shutil.copyfile(GOLDEN / case["reference_cache_file"], cache)
+    helpers.assert_matches(case, case["expected"],
+                           helpers.run_cli(case["input"], case["opts"], tmp_path / "out", cache_in=cache))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", helpers.cases("chain"), ids=lambda c: c["name"])
+def test_cli_cache_chain(case, engine, tmp_path, monkeypatch):
+    monkeypatch.setenv("BREAKFAST_B200_ENGINE", engine)
+    prev = None
+    for k, step in enumerate(case["chain"]):
+        out_cache = tmp_path / f"cache{k}"
+        text = helpers.run_cli(step["input"], case["opts"], tmp_path / f"out{k}", cache_in=prev, cache_out=out_cache)
+        helpers.assert_matches(case, step["expected"], text)
+        prev = out_cache
+
+
+# ------------------------------------------------------------------ C ABI vs oracle on seeded inputs
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("max_dist", [1, 2, 3])
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1000, 4097])
+def test_cluster_and_edges_match_oracle(n, max_dist, engine):
+    indptr, indices, n_cols = synth.generate(n, seed=100 + n).csr()
+    want_labels, want_ne = oracle.cluster(indptr, indices, max_dist)
+    labels, st = _native.cluster_csr(indptr, indices, n_cols, max_dist, engine=engine)
+    assert np.array_equal(labels, want_labels)
+    assert st.n_edges == want_ne and st.n_rows == n
+    assert st.n_components == len(set(want_labels.tolist()))
+    src, dst, st2 = _native.neighbours_csr(indptr, indices, n_cols, max_dist, engine=engine)
+    ws, wd = oracle.edges(indptr, indices, max_dist)
+    assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+    card = np.diff(indptr)
+    h = np.bincount(card)
+    band = sum(int(h[c]) * (int(h[c]) - 1) // 2 for c in range(len(h)))
+    band += sum(int(h[c]) * int(h[c + k]) for k in range(1, max_dist + 1) for c in range(len(h) - k))
+    assert st.pairs_band == band and st.pairs_total == n * (n - 1) // 2
+
+
+@pytest.mark.parametrize("bits", [128, 256, 512, 1024, 2048])
+def test_every_sketch_width_is_exact(bits):
+    indptr, indices, n_cols = synth.generate(3000, seed=77).csr()
+    want, _ = oracle.cluster(indptr, indices, 2)
+    with _native.Context(engine="sketch", sketch_bits=bits) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(2)
+        assert st.bits_per_row == bits
+        assert np.array_equal(ctx.download_labels(), want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_edge_cases(engine):
+    # empty input
+    labels, st = _native.cluster_csr(np.zeros(1, np.int64), np.zeros(0, np.int32), 5, 1, engine=engine)
+    assert labels.size == 0 and st.n_edges == 0
+    # only empty profiles, identical sets, a chain, an isolated row
+    rows = [[], [], [3], [3, 4], [3, 4, 5], [3, 4, 5, 6], [10, 11, 12, 13, 14], [3, 4], [20], []]
+    indptr, indices, n_cols = rows_to_csr(rows, 32)
+    for d in (1, 2, 5):
+        want, _ = oracle.cluster(indptr, indices, d)
+        got, _ = _native.cluster_csr(indptr, indices, n_cols, d, engine=engine)
+        assert np.array_equal(got, want), d
+    # ragged: one very long row next to short ones, long rows one feature apart
+    big = list(range(0, 9000, 2))
+    rows = [big, big + [9001], [1], [1, 3], big[:-1], list(range(50))]
+    indptr, indices, n_cols = rows_to_csr(rows, 9100)
+    want, _ = oracle.cluster(indptr, indices, 1)
+    got, _ = _native.cluster_csr(indptr, indices, n_cols, 1, engine=engine)
+    assert np.array_equal(got, want) and want[1] == 0 and want[4] == 0
+
+
+def test_cardinalities_beyond_the_sort_key_clamp():
+    """rows with more than 65535 features share one (clamped) cardinality key; banding must stay sound"""
+    base = list(range(0, 140000, 2))              # 70000 features
+    rows = [base, base + [1], base[:-1], base[:65535], base[:65534], base[:65535] + [139999], [5]]
+    indptr, indices, n_cols = rows_to_csr(rows, 140000)
+    for engine in ENGINES:
+        want, _ = oracle.cluster(indptr, indices, 1)
+        got, _ = _native.cluster_csr(indptr, indices, n_cols, 1, engine=engine)
+        assert np.array_equal(got, want)
+    assert want.tolist() == [0, 0, 0, 3, 3, 3, 6]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("max_dist", [1, 2])
+def test_incremental_rectangle_matches_oracle(max_dist, engine):
+    indptr, indices, n_cols = synth.generate(3000, seed=5).csr()
+    rng = np.random.default_rng(1)
+    for nq in (0, 1, 40, 1500, 3000):
+        q = np.sort(rng.choice(3000, size=nq, replace=False)).astype(np.int32)
+        src, dst, st = _native.neighbours_csr(indptr, indices, n_cols, max_dist, query_rows=q, engine=engine)
+        if nq == 0:
+            assert src.size == 0
+            continue
+        ws, wd = oracle.edges(indptr, indices, max_dist, queries=q)
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+        assert st.n_query == nq
+
+
+def test_components_api_matches_oracle():
+    rng = np.random.default_rng(3)
+    n = 5000
+    src = rng.integers(0, n, 3000).astype(np.int32)
+    dst = rng.integers(0, n, 3000).astype(np.int32)
+    lens = rng.integers(0, 6, 400)
+    li = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    lm = rng.integers(0, n, int(li[-1])).astype(np.int32)
+    got, ncomp = _native.components(n, src, dst, li, lm)
+    want = oracle.components(n, src, dst, li, lm)
+    assert np.array_equal(got, want) and ncomp == len(set(want.tolist()))
+    got2, _ = _native.components(7)
+    assert got2.tolist() == list(range(7))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_multi_rank_partition_and_merge(world):
+    """every rank takes its cyclic share of the band tiles; merged labels == single-rank labels"""
+    indptr, indices, n_cols = synth.generate(6000, seed=8).csr()
+    single, st1 = _native.cluster_csr(indptr, indices, n_cols, 2)
+    gathered = np.empty((world, 6000), dtype=np.int32)
+    tiles = edges = 0
+    ctxs = []
+    for r in range(world):
+        ctx = _native.Context(engine="sketch")
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(2, rank=r, world=world)
+        gathered[r] = ctx.download_labels()
+        tiles += st.tiles_rank
+        edges += st.n_edges
+        assert st.tiles_band == st1.tiles_band
+        ctxs.append(ctx)
+    assert tiles == st1.tiles_band and edges == st1.n_edges
+    assert not np.array_equal(gathered[0], single)      # a single share is not the answer
+    for ctx in ctxs:
+        ctx.merge_labels_host(gathered)
+        assert np.array_equal(ctx.download_labels(), single)
+        assert ctx.sync().n_components == st1.n_components
+        ctx.close()
+    assert np.array_equal(helpers.merge_labels_cpu(gathered), single)
+
+
+def test_merge_on_device_with_torch_tensors():
+    """the torchrun path: labels -> torch device tensor -> (all-gather) -> merge on device"""
+    torch = pytest.importorskip("torch")
+    assert torch.cuda.is_available()
+    indptr, indices, n_cols = synth.generate(3000, seed=4).csr()
+    single, _ = _native.cluster_csr(indptr, indices, n_cols, 1)
+    tstream = torch.cuda.Stream()          # the library enqueues on this torch stream
+    with torch.cuda.stream(tstream):
+        parts = []
+        ctxs = [_native.Context(stream=tstream.cuda_stream) for _ in range(2)]
+        for r, ctx in enumerate(ctxs):
+            ctx.upload_csr(indptr, indices, n_cols)
+            ctx.run(1, r, 2)
+            t = torch.empty(3000, dtype=torch.int32, device="cuda")
+            ctx.labels_to_device(t.data_ptr())
+            parts.append(t)
+        gathered = torch.stack(parts).contiguous()
+        for ctx in ctxs:
+            ctx.merge_labels_device(gathered.data_ptr(), 2)
+            ctx.sync()
+            assert np.array_equal(ctx.download_labels(), single)
+            ctx.close()
+
+
+def test_candidate_overflow_is_reported_and_recovered():
+    indptr, indices, n_cols = synth.generate(4000, seed=6).csr()
+    want, _ = oracle.cluster(indptr, indices, 2)
+    with _native.Context(cand_capacity=16) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        ctx.run(2)
+        with pytest.raises(_native.NativeError) as e:
+            ctx.sync()
+        assert e.value.code == _native.BF_ERR_OVERFLOW
+        st = ctx.run_sync(2)                               # grows the buffer and reruns
+        assert st.n_candidates > 16
+        assert np.array_equal(ctx.download_labels(), want)
+
+
+def test_call_order_and_argument_errors():
+    with _native.Context() as ctx:
+        with pytest.raises(_native.NativeError) as e:
+            ctx.run(1)
+        assert e.value.code == _native.BF_ERR_STATE
+        with pytest.raises(_native.NativeError):
+            ctx.set_option("sketch_bits", 100)
+        with pytest.raises(_native.NativeError):
+            ctx.upload_csr(np.array([0, 2, 1], np.int64), np.zeros(2, np.int32), 4)
+        indptr, indices, n_cols = synth.generate(10, seed=1).csr()
+        ctx.upload_csr(indptr, indices, n_cols)
+        with pytest.raises(_native.NativeError):
+            ctx.run(1, rank=2, world=2)
+
+
+def test_determinism_and_pinned_memory():
+    indptr, indices, n_cols = synth.generate(20000, seed=12).csr()
+    lib = _native.load()
+    p1, p2 = C.c_void_p(), C.c_void_p()
+    assert lib.bf_pinned_alloc(indptr.nbytes, C.byref(p1)) == 0 and lib.bf_pinned_alloc(indices.nbytes, C.byref(p2)) == 0
+    C.memmove(p1, indptr.ctypes.data, indptr.nbytes)
+    C.memmove(p2, indices.ctypes.data, indices.nbytes)
+    outs = []
+    with _native.Context(want_edges=1) as ctx:
+        ctx.upload_csr_ptr(p1.value, p2.value, len(indptr) - 1, n_cols)
+        for _ in range(3):
+            ctx.run_sync(1)
+            outs.append((ctx.download_labels(), *ctx.download_edges()))
+    lib.bf_pinned_free(p1)
+    lib.bf_pinned_free(p2)
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))
+    want, _ = oracle.cluster(indptr, indices, 1)
+    assert np.array_equal(outs[0][0], want)
+
+
+def test_measured_pipe_peaks_are_plausible():
+    assert _native.measure_peak("popc32") > 1000.0
+    assert _native.measure_peak("lop3") > _native.measure_peak("popc32")
+
+
+# ------------------------------------------------------------------ BASELINE-size properties (1M profiles)
+@pytest.fixture(scope="module")
+def million():
+    prof = synth.generate(1_000_000, seed=1)
+    return prof.csr()
+
+
+def test_million_profiles_properties(million):
+    """At the headline size the oracle cannot run the full job in seconds, so check size-independent
+    properties: exact neighbour sets on a row sample (completeness + soundness), every reported edge
+    is a true edge, labels are canonical fixed points consistent with the edges, two sketch widths
+    agree, and a rerun is identical."""
+    indptr, indices, n_cols = million
+    n = len(indptr) - 1
+    with _native.Context(want_edges=1, sketch_bits=128) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(1)
+        labels = ctx.download_labels()
+        src, dst = ctx.download_edges()
+        ctx.run_sync(1)
+        assert np.array_equal(ctx.download_labels(), labels)
+    assert st.n_edges == src.size and st.pairs_total == n * (n - 1) // 2
+    # canonical labels: fixed points, never larger than the row, constant along every edge
+    assert (labels <= np.arange(n)).all() and np.array_equal(labels[labels], labels)
+    assert np.array_equal(labels[src], labels[dst])
+    # components of exactly these edges (CPU union-find) == labels
+    assert np.array_equal(oracle.components(n, src, dst), labels)
+    # soundness on a sample of reported edges
+    rng = np.random.default_rng(0)
+    for k in rng.choice(src.size, size=min(3000, src.size), replace=False):
+        assert oracle.distance(indptr, indices, int(src[k]), int(dst[k])) <= 1
+    # completeness: exact neighbour sets of 1500 sampled rows, brute force on the CPU
+    q = np.sort(rng.choice(n, size=1500, replace=False)).astype(np.int32)
+    ws, wd = oracle.edges(indptr, indices, 1, queries=q)
+    mask = np.isin(src, q) | np.isin(dst, q)
+    assert edge_set(src[mask], dst[mask]) == edge_set(ws, wd)
+    # a different sketch width gives the same answer
+    with _native.Context(sketch_bits=512) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st2 = ctx.run_sync(1)
+        assert np.array_equal(ctx.download_labels(), labels) and st2.n_edges == st.n_edges

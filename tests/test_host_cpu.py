@@ -1,0 +1,226 @@
+"""Host-side logic of the drop-in interface, on the CPU: feature filtering, vectorisation, dedup,
+output, cache re-indexing, CLI option rules, and the max-dist-0 path end to end.  Mirrors what the
+reference pins in tests/test_filtering.py and the non-distance parts of tests/test_breakfast.py."""
+import re
+from pathlib import Path
+
+import click.testing
+import numpy as np
+import pandas as pd
+import pytest
+
+from breakfast_b200 import breakfast, cache, console, engine
+from tests import helpers
+from tests.helpers import GOLDEN
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# ------------------------------------------------------------------ filter_features
+@pytest.mark.parametrize("features,args,expected", [
+    (["C241T"], (" ", "covsonar_dna", False, False, 0, 0, 1000), ["C241T"]),
+    (["C241T"], (" ", "covsonar_dna", False, False, 250, 0, 1000), [""]),
+    ([""], (" ", "covsonar_dna", False, False, 250, 0, 1000), [""]),
+    (["  "], (" ", "covsonar_dna", False, False, 250, 0, 1000), [""]),
+    (["C241T del:10:1 G5343TT"], (" ", "covsonar_dna", False, True, 0, 0, 1000), ["C241T G5343TT"]),
+    (["C241T del:10:1 G5343TT"], (" ", "covsonar_dna", True, False, 0, 0, 1000), ["C241T del:10:1"]),
+    (["C241T del:10:1 G5343TT"], (" ", "covsonar_dna", True, True, 0, 0, 1000), ["C241T"]),
+    (["C241T del:10:1 G5343TT C900T"], (" ", "covsonar_dna", True, True, 250, 150, 1000), [""]),
+    (["S:N501Y S:del:69:2 S:A222VV"], (" ", "covsonar_aa", True, True, 0, 0, 1000), ["S:N501Y"]),
+    (["S:N501Y S:H69- S:Y144*"], (" ", "nextclade_aa", True, True, 0, 0, 1000), ["S:N501Y S:Y144*"]),
+    (["C241T,1000-1010,1200,300:ACG"], (",", "nextclade_dna", True, True, 0, 0, 30000), ["C241T"]),
+    (["C241T,1000-1010,1200,300:ACG"], (",", "nextclade_dna", False, True, 0, 0, 30000), ["C241T,300:ACG"]),
+    (["a  b x"], (" ", "raw", True, True, 10, 10, 100), ["a b x"]),
+])
+def test_filter_features(features, args, expected):
+    assert breakfast.filter_features(features, *args) == expected
+
+
+def test_filter_trimming_is_inclusive_and_substitutions_only():
+    f = ["C264T C265T C29674T C29675T del:100:5 A100AT"]
+    out = breakfast.filter_features(f, " ", "covsonar_dna", False, False, 264, 228, 29903)
+    assert out == ["C265T C29674T del:100:5 A100AT"]
+
+
+def test_filter_noop_returns_the_same_object_and_keeps_invalid_tokens():
+    f = pd.Series(["bogus  C241T"])
+    assert breakfast.filter_features(f, " ", "covsonar_dna", False, False, 0, 0, 1000) is f
+
+
+def test_filter_reports_invalid_tokens(capsys):
+    out = breakfast.filter_features(["C241T bogus  G1A"], " ", "covsonar_dna", True, True, 0, 0, 1000)
+    assert out == ["C241T G1A"]
+    printed = capsys.readouterr().out
+    assert "Skipping invalid feature: 'bogus'" in printed and "Skipping invalid feature: ''" in printed
+
+
+def test_filter_unknown_type_exits():
+    with pytest.raises(SystemExit):
+        breakfast.filter_features(["x"], " ", "nope", True, True, 0, 0, 10)
+
+
+# ------------------------------------------------------------------ vectorisation
+def test_sparse_matrix_ignores_empty_features():
+    m = breakfast.sparse_feature_matrix(["", "C241T"], " ")
+    assert m.shape == (2, 1)
+    assert m[0].count_nonzero() == 0 and m[1].count_nonzero() == 1
+
+
+def test_sparse_matrix_vocabulary_order_and_repeats():
+    m = breakfast.sparse_feature_matrix(pd.Series(["b a b", "a  c", float("nan")]), " ")
+    assert m.shape == (3, 3) and m.dtype == np.int64
+    assert m.indptr.tolist() == [0, 3, 5, 5]
+    assert m.indices.tolist() == [0, 1, 0, 1, 2]          # b=0, a=1, c=2; the repeat is kept
+    assert np.asarray(m.sum(axis=1)).ravel().tolist() == [3, 2, 0]
+
+
+def test_sparse_matrix_all_empty_raises_like_the_reference():
+    with pytest.raises(ValueError, match="unable to infer matrix dimensions"):
+        breakfast.sparse_feature_matrix(["", ""], " ")
+
+
+def test_thermometer_coding_equals_l1_on_counts():
+    feats = ["A A B", "A B", "B A", "A A A B", "", "C"]
+    indptr, indices, n_cols = engine.binary_csr(feats, " ")
+    rows = [set(indices[indptr[i]:indptr[i + 1]].tolist()) for i in range(len(feats))]
+    for i in range(len(feats)):
+        assert sorted(rows[i]) == indices[indptr[i]:indptr[i + 1]].tolist()  # ascending, unique
+    from collections import Counter
+    counts = [Counter(t for t in f.split(" ") if t) for f in feats]
+    for i in range(len(feats)):
+        for j in range(len(feats)):
+            l1 = sum(abs(counts[i][k] - counts[j][k]) for k in set(counts[i]) | set(counts[j]))
+            assert len(rows[i] ^ rows[j]) == l1
+    assert n_cols == 3 + 2  # A, B, C + (A,1), (A,2)
+
+
+# ------------------------------------------------------------------ dedup / output
+def test_collapse_duplicates_groups_by_string_in_first_appearance_order(capsys):
+    meta = pd.DataFrame({"id": ["s1", "s2", "s3", "s4", "s5"], "feature": ["x y", "z", "x y", "y x", "z"]})
+    nd = breakfast.collapse_duplicates(meta)
+    assert nd.columns.tolist() == ["id", "feature"]
+    assert nd["feature"].tolist() == ["x y", "z", "y x"]   # permutations stay separate profiles
+    assert nd["id"].tolist() == [("s1", "s3"), ("s2", "s5"), ("s4",)]
+    out = capsys.readouterr().out
+    assert "Number of duplicates: 2" in out and "Number of unique sequences: 3" in out
+
+
+def test_read_input_rejects_duplicate_ids():
+    with pytest.raises(ValueError, match="Duplicate sequence identifiers"):
+        breakfast.read_input(GOLDEN / "reference" / "duplicate-ids.tsv", "\t", "accession", "dna_profile")
+
+
+def test_read_input_na_profile_is_the_empty_profile(tmp_path):
+    p = tmp_path / "t.tsv"
+    p.write_text("accession\tdna_profile\na\tNA\nb\t\nc\tC300T\n")
+    t = breakfast.read_input(p, "\t", "accession", "dna_profile")
+    assert t["feature"].tolist() == ["", "", "C300T"]
+
+
+def test_write_output_renumbers_by_first_appearance(tmp_path):
+    orig = pd.DataFrame({"id": ["c", "a", "d", "b", "e"], "feature": ["."] * 5})
+    col = np.empty(3, dtype=object)
+    col[:] = [7, pd.NA, 3]
+    nodups = pd.DataFrame({"id": [("a", "b"), ("c",), ("d", "e")], "feature": ["x", "y", "z"], "cluster_id": col})
+    breakfast.write_output(nodups, orig, tmp_path / "deep" / "out")
+    assert (tmp_path / "deep" / "out" / "clusters.tsv").read_text() == "id\tcluster_id\nc\t\na\t1\nd\t2\nb\t1\ne\t2\n"
+
+
+# ------------------------------------------------------------------ cache re-indexing
+def test_cache_map_and_update_with_ghost_list():
+    cached = pd.Series(["A", "A g", "A g h", "Q"])
+    new = pd.Series(["A g h", "N", "A"])                    # "A g" and "Q" vanished, "N" is new
+    fmap = cache.map_features(cached, new)
+    assert fmap.index.tolist() == sorted(["A", "A g", "A g h", "Q", "N"])
+    assert np.array(cache.find_new(fmap)).astype(int).tolist() == [1]
+    assert sorted(np.array(cache.find_deleted(fmap)).astype(int).tolist()) == [1, 3]
+    neigh = [np.array([0, 1]), np.array([0, 1, 2]), [1, 2], np.array([3])]
+    # list of row 1 ("A g", gone) keeps chaining A and "A g h": the ghost list
+    assert cache.update_neighbours(neigh, fmap) == [[2], [2, 0], [0]]
+    li, lm = cache.update_neighbours_csr(neigh, fmap)
+    assert li.tolist() == [0, 1, 3, 4] and lm.tolist() == [2, 2, 0, 0]
+
+
+def test_cache_roundtrip_and_validation(tmp_path, capsys):
+    meta = pd.DataFrame({"id": [("a",), ("b", "c")], "feature": ["x", "y"], "extra": [1, 2]})
+    f = tmp_path / "sub" / "cache.pkl.gz"
+    cache.save(f, [np.array([0, 1]), [1]], meta, 2)
+    got = cache.load(f, 2)
+    assert got["max_dist"] == 2 and got["meta"].columns.tolist() == ["id", "feature"]
+    assert [list(map(int, x)) for x in got["neigh"]] == [[0, 1], [1]]
+    with pytest.raises(UnboundLocalError):
+        cache.load(f, 1)
+    with pytest.raises(TypeError):
+        cache.load(None, 1)
+
+
+def test_reference_written_cache_is_readable():
+    got = cache.load(GOLDEN / "synthetic" / "ref_testfile_dist1.cache", 1)
+    assert set(got) == {"max_dist", "version", "neigh", "meta"}
+    assert got["meta"]["feature"].size == 3
+
+
+# ------------------------------------------------------------------ CLI surface
+@pytest.fixture
+def runner():
+    return click.testing.CliRunner()
+
+
+def test_cli_help_lists_every_reference_option(runner):
+    res = runner.invoke(console.main, ["--help"])
+    assert res.exit_code == 0
+    for opt in ("--input-file", "--sep", "--outdir", "--max-dist", "--min-cluster-size", "--input-cache",
+                "--output-cache", "--id-col", "--clust-col", "--var-type", "--sep2", "--trim-start", "--trim-end",
+                "--reference-length", "--skip-del", "--no-skip-del", "--skip-ins", "--no-skip-ins", "--jobs",
+                "--version"):
+        assert opt in res.output, opt
+
+
+@pytest.mark.parametrize("extra", [["--clust-col", "somethingmissing"], ["--id-col", "somethingmissing"]])
+def test_cli_missing_column_fails(runner, tmp_path, extra):
+    res = runner.invoke(console.main, ["--input-file", str(GOLDEN / "reference" / "testfile.tsv"), "--outdir",
+                                       str(tmp_path), "--max-dist", "0"] + extra)
+    assert res.exit_code != 0
+
+
+def test_cli_duplicate_ids_fail(runner, tmp_path):
+    res = runner.invoke(console.main, ["--input-file", str(GOLDEN / "reference" / "duplicate-ids.tsv"), "--outdir",
+                                       str(tmp_path), "--max-dist", "0"])
+    assert res.exit_code != 0 and isinstance(res.exception, ValueError)
+
+
+@pytest.mark.parametrize("extra", [["--trim-start", "10"], ["--trim-end", "10"], ["--skip-del"], ["--skip-ins"]])
+def test_cli_non_dna_rejects_explicit_dna_options(runner, tmp_path, extra):
+    res = runner.invoke(console.main, ["--input-file", str(GOLDEN / "reference" / "testfile.tsv"), "--outdir",
+                                       str(tmp_path), "--max-dist", "0", "--var-type", "raw"] + extra)
+    assert res.exit_code != 0 and "non-DNA" in res.output
+
+
+def test_cli_trim_beyond_reference_fails(runner, tmp_path):
+    res = runner.invoke(console.main, ["--input-file", str(GOLDEN / "reference" / "testfile.tsv"), "--outdir",
+                                       str(tmp_path), "--max-dist", "0", "--trim-start", "40000"])
+    assert res.exit_code != 0
+
+
+@pytest.mark.parametrize("case", [c for c in helpers.cases("plain") if c["opts"].get("max_dist") == 0],
+                         ids=lambda c: c["name"])
+def test_cli_max_dist_zero_goldens(case, tmp_path):
+    """--max-dist 0 is a host-only path in the reference too (breakfast.py:343-364): no GPU needed."""
+    helpers.assert_matches(case, case["expected"], helpers.run_cli(case["input"], case["opts"], tmp_path))
+
+
+# ------------------------------------------------------------------ no CPU fallback, no oracle in the product
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|ref_port|liboracle", re.M)
+    for f in list((ROOT / "breakfast_b200").rglob("*.py")) + list((ROOT / "breakfast").rglob("*.py")) + \
+            list((ROOT / "breakfast_b200" / "csrc").glob("*")):
+        assert not pat.search(f.read_text(errors="ignore")), f"{f} refers to the oracle"
+
+
+def test_cluster_without_gpu_fails_loudly(tmp_path):
+    from breakfast_b200 import _native
+    if _native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    meta = pd.DataFrame({"id": [("a",), ("b",)], "feature": ["C300T", "C300T G400A"]})
+    with pytest.raises(_native.NativeError):
+        breakfast.cluster(meta, " ", 1, 1, None, None)

@@ -23,7 +23,9 @@ class Stats(C.Structure):
         "n_rows", "n_query", "n_cols", "nnz", "bits_per_row", "pairs_total", "pairs_band", "pairs_evaluated",
         "tiles_total", "tiles_band", "tiles_rank", "n_candidates", "n_edges", "n_components")] + [
         (n, C.c_double) for n in ("ms_h2d", "ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge",
-                                  "ms_d2h", "ms_total")]
+                                  "ms_d2h", "ms_total")] + [
+        ("runs_since_sync", C.c_int64), ("kernel_launches", C.c_int64), ("ms_pairs_sum", C.c_double),
+        ("ms_total_sum", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
