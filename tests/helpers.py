@@ -88,35 +88,4 @@ def merge_labels_cpu(gathered: np.ndarray) -> np.ndarray:
     return oracle.components(n, src, dst)
 
 
-class OracleEngine:
-    """Stand-in for breakfast_b200.engine.components_* backed by the CPU oracle.  CPU tests use it to
-    exercise the host pipeline (parsing, dedup, cache re-indexing, labelling, output) without a GPU.
-    Test infrastructure only: installed with monkeypatch, never reachable from the product."""
-
-    @staticmethod
-    def full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None):
-        import oracle
-        from breakfast_b200.engine import ClusterResult
-        src, dst = oracle.edges(indptr, indices, max_dist)
-        labels = oracle.components(len(indptr) - 1, src, dst)
-        return ClusterResult(labels, {}, (src, dst) if want_edges else None)
-
-    @staticmethod
-    def incremental(indptr, indices, n_cols, max_dist, new_rows, list_indptr, list_members, want_edges=False,
-                    device=None, engine=None):
-        import oracle
-        from breakfast_b200.engine import ClusterResult
-        new_rows = np.unique(np.asarray(new_rows, dtype=np.int32))
-        n = len(indptr) - 1
-        if new_rows.size:
-            src, dst = oracle.edges(indptr, indices, max_dist, queries=new_rows)
-        else:
-            src = dst = np.zeros(0, np.int32)
-        labels = oracle.components(n, src, dst, list_indptr, list_members)
-        return ClusterResult(labels, {}, (src, dst) if want_edges else None)
-
-    @classmethod
-    def install(cls, monkeypatch):
-        from breakfast_b200 import engine
-        monkeypatch.setattr(engine, "components_full", cls.full)
-        monkeypatch.setattr(engine, "components_incremental", cls.incremental)
+from oracle.engine_standin import OracleEngine  # noqa: E402,F401  (re-exported for the tests)
