@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
     ap.add_argument("--engine", default="sketch", choices=["sketch", "full"])
+    ap.add_argument("--two-level", type=int, default=1, choices=[0, 1])
     ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -212,7 +213,8 @@ def main():
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits)
+    ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits,
+                          two_level=args.two_level)
     ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
     runner = RankRunner(ctx, n, rank, world)
 
@@ -243,7 +245,7 @@ def main():
     # per-launch duration of the dominant kernel over the timed region (CUDA events on the launching stream)
     runs = max(1, min(st.runs_since_sync, 128))
     ms_pairs = st.ms_pairs_sum / runs
-    popc_per_launch = st.pairs_evaluated * (st.bits_per_row // 32)
+    popc_per_launch = st.popc32_executed   # level-1 fold (1 per pair) + full-width pass of the surviving warps
     achieved = popc_per_launch / (ms_pairs * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
@@ -299,7 +301,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD if n == N_PROFILES else f"{n} profiles (override)", "max_dist": MAX_DIST,
-                       "engine": args.engine, "bits_per_row": st.bits_per_row, "n_cols": n_cols, "nnz": int(indices.size),
+                       "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level),
+                       "l2_warp_items": st.l2_warp_items, "pairs_evaluated": st.pairs_evaluated, "n_cols": n_cols, "nnz": int(indices.size),
                        "candidate_pairs": st.pairs_band, "pairs_total": st.pairs_total, "tiles_band": st.tiles_band,
                        "edges": None if world > 1 else st.n_edges, "components": st.n_components,
                        "l2_policy": "inputs larger than L2 (CSR 360 MB + per-step rebuilt bitsets); no explicit flush",

@@ -92,6 +92,8 @@ struct bf_ctx {
     int want_edges = 0;
     int64_t cand_capacity = 0;  // 0 = auto
     int blocks_per_sm = 0;      // 0 = occupancy
+    int two_level = 1;
+    int64_t items_capacity = 0;  // 0 = auto
 
     // problem
     bool uploaded = false, ran = false, has_query = false;
@@ -102,12 +104,13 @@ struct bf_ctx {
     int max_dist = 0, rank = 0, world = 1;
     int K4 = 1, n_chunks = 1;
     int64_t bits_per_row = 0, tilesA = 0, tilesB = 0;
-    unsigned long long cand_cap_used = 0;
+    unsigned long long cand_cap_used = 0, items_cap_used = 0;
+    bool ran_two_level = false;
     float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
 
     DevBuf indptr, indices, query_rows, is_query;
-    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts;
-    DevBuf bitsA, bitsB, jlo, wprefix, nwork, cand, edges, parent, labels, counters, scratch, scratch2;
+    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
+    DevBuf bitsA, bitsB, jlo, wprefix, nwork, items, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
     // per-run event ring so that bf_sync can report sums over all runs since the last sync
@@ -127,7 +130,7 @@ int set_device(bf_ctx* c) {
 }
 
 // rows sorted by (clamped) cardinality: keys[0]/vals[0] hold the result (two ping-pong passes)
-int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2]) {
+int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2], int side) {
     if (n == 0) return BF_OK;
     const int nblocks = (int)ceil_div(n, SORT_ITEMS);
     for (int i = 0; i < 2; ++i) {
@@ -135,20 +138,23 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
         TRY(vals[i].ensure(n * sizeof(int32_t)));
     }
     TRY(c->sort_counts.ensure((size_t)256 * nblocks * sizeof(uint32_t)));
+    TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
+    uint32_t* max_key = c->sort_max.as<uint32_t>() + side;
+    CK(cudaMemsetAsync(max_key, 0, sizeof(uint32_t), c->stream));
     k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(), rows_dev, n,
-                                                          keys[0].as<uint32_t>(), vals[0].as<int32_t>());
+                                                          keys[0].as<uint32_t>(), vals[0].as<int32_t>(), max_key);
     CKLC(c);
     for (int pass = 0; pass < 2; ++pass) {
         const int in = pass & 1, out = in ^ 1, shift = 8 * pass;
         k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
-                                                    c->sort_counts.as<uint32_t>(), nblocks);
+                                                    c->sort_counts.as<uint32_t>(), nblocks, max_key);
         CKLC(c);
         k_exclusive_scan<uint32_t><<<1, 1024, 0, c->stream>>>(c->sort_counts.as<uint32_t>(),
-                                                              (int64_t)256 * nblocks, nullptr);
+                                                              (int64_t)256 * nblocks, nullptr, max_key, shift);
         CKLC(c);
         k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
                                                        c->sort_counts.as<uint32_t>(), nblocks,
-                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>());
+                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>(), max_key);
         CKLC(c);
     }
     return BF_OK;
@@ -177,26 +183,33 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
     return BF_OK;
 }
 
-template <int K4>
+template <int K4, int STAGES, bool TWO_LEVEL>
 int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int triangular) {
-    using L = PairSmem<K4>;
+    using L = PairSmem<K4, STAGES>;
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
-        CK(cudaFuncSetAttribute(k_pairs<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes));
+        CK(cudaFuncSetAttribute(k_pairs<K4, STAGES, TWO_LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes));
         attr_set[c->device & 63] = true;
     }
     int bps = c->blocks_per_sm;
     if (bps <= 0) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pairs<K4>, PAIR_THREADS, L::kTotalBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pairs<K4, STAGES, TWO_LEVEL>, PAIR_THREADS, L::kTotalBytes));
         bps = std::max(1, std::min(bps, 4));
     }
     const unsigned grid = (unsigned)(c->num_sms * bps);
-    k_pairs<K4><<<grid, PAIR_THREADS, L::kTotalBytes, c->stream>>>(
-        A, B, c->n_chunks, nA, nB, c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(), c->tilesA,
-        c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank, c->world, c->cand.as<uint2>(),
-        c->cand_cap_used, c->counters.as<DevCounters>());
+    k_pairs<K4, STAGES, TWO_LEVEL><<<grid, PAIR_THREADS, L::kTotalBytes, c->stream>>>(
+        A, B, c->n_chunks, nA, nB, c->items.as<int2>(), c->items_cap_used, c->wprefix.as<unsigned long long>(),
+        c->jlo.as<int32_t>(), c->tilesA, c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank,
+        c->world, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
+}
+
+int dispatch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
+    const bool two = c->ran_two_level;
+    if (c->K4 == 1) return two ? launch_pairs<1, 8, true>(c, A, B, nA, nB, tri) : launch_pairs<1, 8, false>(c, A, B, nA, nB, tri);
+    if (c->K4 == 2) return two ? launch_pairs<2, 8, true>(c, A, B, nA, nB, tri) : launch_pairs<2, 8, false>(c, A, B, nA, nB, tri);
+    return two ? launch_pairs<4, 4, true>(c, A, B, nA, nB, tri) : launch_pairs<4, 4, false>(c, A, B, nA, nB, tri);
 }
 
 int finish_labels(bf_ctx* c) {
@@ -285,7 +298,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->indptr, &c->indices, &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->bitsA, &c->bitsB, &c->jlo, &c->wprefix, &c->nwork, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->jlo, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -310,6 +323,11 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "cand_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "cand_capacity must be >= 0");
         c->cand_capacity = value;
+    } else if (k == "two_level") {
+        c->two_level = value ? 1 : 0;
+    } else if (k == "items_capacity") {
+        if (value < 0) return fail(BF_ERR_INVALID, "items_capacity must be >= 0");
+        c->items_capacity = value;
     } else if (k == "blocks_per_sm") {
         if (value < 0 || value > 8) return fail(BF_ERR_INVALID, "blocks_per_sm must be in [0, 8]");
         c->blocks_per_sm = (int)value;
@@ -402,6 +420,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     }
     c->tilesA = ceil_div(nA, TILE);
     c->tilesB = ceil_div(nB, TILE);
+    c->ran_two_level = c->engine == BF_ENGINE_SKETCH && c->n_chunks == 1 && c->two_level;
 
     cudaEvent_t* ring = c->ring[c->runs_since_sync % bf_ctx::kRing];
     CK(cudaEventRecord(c->ev[0], c->stream));
@@ -420,8 +439,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     DevBuf* valsA = c->has_query ? c->valsA : c->valsB;
     if (active) {
         // ---- K2: sort by cardinality
-        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB));
-        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA));
+        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0));
+        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1));
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
     if (active) {
@@ -439,13 +458,27 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             c->jlo.as<int32_t>(), c->wprefix.as<unsigned long long>());
         CKLC(c);
         CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
-        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>());
+        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
         CKLC(c);
         DevCounters* dc = c->counters.as<DevCounters>();
         k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
         CKLC(c);
         if (c->has_query) {
             k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, keysA[0].as<uint32_t>(), nA, max_dist, &dc->band_aa);
+            CKLC(c);
+        }
+        // explicit work list for the producer (bounded; items beyond it fall back to a binary search)
+        {
+            const unsigned long long worst = c->has_query ? (unsigned long long)c->tilesA * c->tilesB
+                                                          : (unsigned long long)c->tilesB * (c->tilesB + 1) / 2;
+            unsigned long long icap = c->items_capacity > 0 ? (unsigned long long)c->items_capacity
+                                                            : std::min<unsigned long long>(worst, 1ull << 24);
+            icap = std::max<unsigned long long>(icap, 1);
+            TRY(c->items.ensure((size_t)icap * sizeof(int2)));
+            c->items_cap_used = icap;
+            k_expand_items<<<c->num_sms * 8, 256, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(),
+                                                                  c->tilesA, c->nwork.as<unsigned long long>(), icap,
+                                                                  c->items.as<int2>());
             CKLC(c);
         }
         // candidate buffer
@@ -462,9 +495,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         const uint4* A = (c->has_query ? c->bitsA : c->bitsB).as<uint4>();
         const uint4* B = c->bitsB.as<uint4>();
         const int tri = c->has_query ? 0 : 1;
-        if (c->K4 == 1) TRY(launch_pairs<1>(c, A, B, nA, nB, tri));
-        else if (c->K4 == 2) TRY(launch_pairs<2>(c, A, B, nA, nB, tri));
-        else TRY(launch_pairs<4>(c, A, B, nA, nB, tri));
+        TRY(dispatch_pairs(c, A, B, nA, nB, tri));
     }
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaEventRecord(ring[2], c->stream));
@@ -585,6 +616,12 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
         st->n_candidates = (int64_t)h.n_cand;
         st->n_edges = (int64_t)h.n_edges;
         st->n_components = h.n_comp;
+        st->l2_warp_items = (int64_t)h.l2_warp_items;
+        {
+            const int64_t words = c->bits_per_row / 32;
+            st->popc32_executed = c->ran_two_level ? st->pairs_evaluated + (int64_t)h.l2_warp_items * 1024 * words
+                                                   : st->pairs_evaluated * words;
+        }
         float ms = 0;
         st->ms_h2d = c->ms_h2d;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); st->ms_sort = ms;

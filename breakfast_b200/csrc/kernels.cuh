@@ -29,7 +29,6 @@ namespace bf {
 constexpr int TILE = 128;              // rows per tile (both operands)
 constexpr uint32_t KEY_CLAMP = 65535;  // cardinality sort key is clamped (1-Lipschitz, band test stays sound)
 constexpr int SORT_ITEMS = 1024;       // rows per block in the radix passes
-constexpr int PAIR_STAGES = 4;         // smem ring depth of the pair kernel
 constexpr int PAIR_CONSUMER_WARPS = 16;
 constexpr int PAIR_THREADS = (PAIR_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 
@@ -38,6 +37,7 @@ struct DevCounters {
     unsigned long long n_edges;     // verified edges
     unsigned long long band_ab;     // ordered in-band (a,b) count, A side vs B side (incl. self)
     unsigned long long band_aa;     // ordered in-band (a,a') count inside the A side (rectangle runs)
+    unsigned long long l2_warp_items;  // (warp, work item) pairs of the pair kernel that needed the full-width pass
     unsigned int n_comp;
     unsigned int pad;
 };
@@ -46,18 +46,27 @@ struct DevCounters {
 // K2: cardinality keys + stable LSD radix sort (2 x 8 bits) — deterministic permutation
 // ------------------------------------------------------------------------------------------
 __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
-                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                            uint32_t* __restrict__ max_key) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    int32_t r = rows ? rows[q] : (int32_t)q;
-    int64_t c = indptr[r + 1] - indptr[r];
-    keys[q] = c > (int64_t)KEY_CLAMP ? KEY_CLAMP : (uint32_t)c;
-    vals[q] = r;
+    uint32_t k = 0;
+    if (q < n) {
+        int32_t r = rows ? rows[q] : (int32_t)q;
+        int64_t c = indptr[r + 1] - indptr[r];
+        k = c > (int64_t)KEY_CLAMP ? KEY_CLAMP : (uint32_t)c;
+        keys[q] = k;
+        vals[q] = r;
+    }
+    // warp max -> one atomic per warp; a radix pass whose digits are all zero is skipped
+    k = __reduce_max_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(max_key, k);
 }
 
 // counts[digit * nblocks + block] = number of rows of `block` whose digit == digit
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
-                                                   uint32_t* __restrict__ counts, int nblocks) {
+                                                   uint32_t* __restrict__ counts, int nblocks,
+                                                   const uint32_t* __restrict__ max_key) {
+    if ((*max_key >> shift) == 0) return;  // every digit of this pass is 0: identity pass
     __shared__ uint16_t dig[SORT_ITEMS];
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
     const int m = (int)min((int64_t)SORT_ITEMS, n - base);
@@ -74,11 +83,19 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
                                                       const int32_t* __restrict__ vals, int64_t n, int shift,
                                                       const uint32_t* __restrict__ offsets, int nblocks,
                                                       uint32_t* __restrict__ keys_out,
-                                                      int32_t* __restrict__ vals_out) {
+                                                      int32_t* __restrict__ vals_out,
+                                                      const uint32_t* __restrict__ max_key) {
     __shared__ uint32_t sk[SORT_ITEMS];
     __shared__ int32_t sv[SORT_ITEMS];
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
     const int m = (int)min((int64_t)SORT_ITEMS, n - base);
+    if ((*max_key >> shift) == 0) {  // identity pass: plain copy
+        for (int i = threadIdx.x; i < m; i += 256) {
+            keys_out[base + i] = keys[base + i];
+            vals_out[base + i] = vals[base + i];
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < m; i += 256) {
         sk[i] = keys[base + i];
         sv[i] = vals[base + i];
@@ -96,18 +113,28 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     }
 }
 
-// Single-block exclusive scan (in place), total written to *total_out (may be null).
+// Single-block exclusive scan (in place), 8 elements per thread per sweep; total -> *total_out (may be
+// null).  `skip_if_zero` (may be null): when *skip_if_zero >> skip_shift == 0 the scan is not needed.
 template <typename T>
-__global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, int64_t n, T* total_out) {
+__global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, int64_t n, T* total_out,
+                                                         const uint32_t* __restrict__ skip_if_zero, int skip_shift) {
+    if (skip_if_zero && (*skip_if_zero >> skip_shift) == 0) return;
+    constexpr int PER = 8;
     __shared__ T warp_sums[32];
     __shared__ T carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        T v = i < n ? data[i] : (T)0;
-        T x = v;
+    for (int64_t base = 0; base < n; base += 1024 * PER) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * PER;
+        T v[PER];
+        T local = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            v[k] = (i0 + k < n) ? data[i0 + k] : (T)0;
+            local += v[k];
+        }
+        T x = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             T y = __shfl_up_sync(0xffffffffu, x, o);
@@ -116,18 +143,22 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, i
         if (lane == 31) warp_sums[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            T s = warp_sums[lane];
+            T t = warp_sums[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                T y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += y;
+                T y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
             }
-            warp_sums[lane] = s;  // inclusive over warps
+            warp_sums[lane] = t;  // inclusive over warps
         }
         __syncthreads();
-        T carry = carry_s;
-        T excl = carry + (warp ? warp_sums[warp - 1] : (T)0) + (x - v);
-        if (i < n) data[i] = excl;
+        const T carry = carry_s;
+        T run = carry + (warp ? warp_sums[warp - 1] : (T)0) + (x - local);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            if (i0 + k < n) data[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
@@ -214,6 +245,8 @@ __device__ __forceinline__ uint32_t fold_hash(uint32_t col, int log2m) {
 
 // SKETCH: one block per tile; the folded tile is assembled in shared memory (XOR-toggle per feature)
 // and written out as one coalesced block.  HBM traffic: reads 4*nnz + 12*N bytes, writes N*m/8 bytes.
+// Each warp owns 16 rows; lanes 0-15 fetch perm/indptr of all 16 rows at once (one dependent-load
+// chain per warp, not per row), then the warp streams the rows' column lists.
 __global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__ indptr,
                                                      const int32_t* __restrict__ indices,
                                                      const int32_t* __restrict__ perm, int64_t n, int log2m,
@@ -221,16 +254,24 @@ __global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__
     extern __shared__ uint32_t tile_words[];  // n_chunks*K4*TILE*4 words
     const int words_per_tile = n_chunks * K4 * TILE * 4;
     for (int i = threadIdx.x; i < words_per_tile; i += 256) tile_words[i] = 0u;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
-    for (int row = warp; row < TILE; row += 8) {
-        int64_t p = tile * TILE + row;
-        if (p >= n) break;
-        int32_t r = perm[p];
-        int64_t b = indptr[r], e = indptr[r + 1];
-        for (int64_t k = b + lane; k < e; k += 32) {
-            uint32_t h = fold_hash((uint32_t)indices[k], log2m);
+    int64_t my_b = 0, my_e = 0;
+    if (lane < TILE / 8) {
+        const int64_t p = tile * TILE + warp + 8 * lane;
+        if (p < n) {
+            const int32_t r = perm[p];
+            my_b = indptr[r];
+            my_e = indptr[r + 1];
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < TILE / 8; ++k) {
+        const int64_t b = __shfl_sync(0xffffffffu, my_b, k), e = __shfl_sync(0xffffffffu, my_e, k);
+        const int row = warp + 8 * k;
+        for (int64_t q = b + lane; q < e; q += 32) {
+            const uint32_t h = fold_hash((uint32_t)__ldg(&indices[q]), log2m);
             atomicXor(&tile_words[word_offset(0, n_chunks, K4, (int)(h >> 5), row)], 1u << (h & 31));
         }
     }
@@ -296,39 +337,64 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 // ------------------------------------------------------------------------------------------
+// K2c: explicit work list.  items[w] = (I, J) for every band tile pair, so that the pair kernel's
+// producer needs one load per item instead of a binary search.
+// ------------------------------------------------------------------------------------------
+__global__ void k_expand_items(const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo,
+                               int64_t tilesA, const unsigned long long* __restrict__ n_work,
+                               unsigned long long cap, int2* __restrict__ items) {
+    const unsigned long long W = min(*n_work, cap);
+    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < W;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = tilesA - 1;  // largest I with wprefix[I] <= w
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
+        }
+        items[w] = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: tiled XOR/POPC pair kernel.
 //   persistent grid; work item = one band tile pair (I, J); item w of the global list belongs to
 //   rank (w % world); block b takes this rank's items b, b+grid, ...
-//   warp 16 = producer: one lane maps w -> (I,J) and issues two bulk-async copies per chunk into a
-//   4-stage shared-memory ring, completion on an mbarrier (expect_tx).
+//   warp 16 = producer: 32 lanes fetch 32 work items at once, lane 0 issues two bulk-async (TMA)
+//   copies per chunk into a STAGES-deep shared-memory ring, completion on an mbarrier (expect_tx).
 //   warps 0-15 = consumers: thread (warp, lane) owns the 8x4 pairs (warp+16i, lane+32j); per
 //   16-byte k-group: 4 LDS.128 of B kept in registers, 8 broadcast LDS.128 of A, 128
 //   LOP3(xor)+POPC+IADD.  Threshold in the epilogue; the (rare) hits go to a global candidate list.
 //   Algorithmic work per evaluated pair: bits_per_row/32 POPC32 (+ as many XOR).
+//
+//   TWO_LEVEL (single-chunk sketches): every row's sketch is first XOR-folded once more to 32 bits
+//   (fold of a fold is still a lower bound of |A xor B|), so level 1 costs ONE popc per pair and
+//   keeps only a running minimum; a warp whose 1024 pairs all exceed the threshold is done.  Only
+//   warps with a level-1 survivor run the full-width pass above (counted in l2_warp_items).
 // ------------------------------------------------------------------------------------------
-template <int K4>
+template <int K4, int STAGES>
 struct PairSmem {
     static constexpr int kOperandBytes = K4 * TILE * 16;
     static constexpr int kStageBytes = 2 * kOperandBytes;
-    static constexpr int kRingBytes = PAIR_STAGES * kStageBytes;
-    static constexpr int kTotalBytes = kRingBytes + PAIR_STAGES * (8 + 8 + 8);
+    static constexpr int kRingBytes = STAGES * kStageBytes;
+    static constexpr int kTotalBytes = kRingBytes + STAGES * (8 + 8 + 8);
 };
 
-template <int K4>
+template <int K4, int STAGES, bool TWO_LEVEL>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_chunks, int64_t nA, int64_t nB,
+        const int2* __restrict__ items, unsigned long long items_cap,
         const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo, int64_t tilesA,
         const unsigned long long* __restrict__ n_work, int threshold, int triangular, int rank, int world,
         uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
-    using L = PairSmem<K4>;
+    using L = PairSmem<K4, STAGES>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
-    uint64_t* empty_bar = full_bar + PAIR_STAGES;
-    int2* meta = reinterpret_cast<int2*>(empty_bar + PAIR_STAGES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    int2* meta = reinterpret_cast<int2*>(empty_bar + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PAIR_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
         }
@@ -342,30 +408,31 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
 
     if (warp == PAIR_CONSUMER_WARPS) {
         // ------------------------------- producer -------------------------------
-        // All 32 lanes map one work item each to its tile pair (binary search on the work prefix:
-        // 32 independent chains of L2 loads in flight), then lane 0 issues the copies item by item.
         uint32_t it = 0;
         for (unsigned long long k0 = 0;; k0 += 32) {
-            const unsigned long long w = first + (k0 + lane) * stride;
             if (first + k0 * stride >= W) break;
-            int I = 0, J = 0;
+            const unsigned long long w = first + (k0 + lane) * stride;
+            int2 mine = make_int2(0, 0);
             if (w < W) {
-                int64_t lo = 0, hi = tilesA - 1;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi + 1) >> 1;
-                    if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
+                if (w < items_cap) {
+                    mine = __ldg(&items[w]);
+                } else {  // beyond the expanded table (huge bands): map w -> (I, J) by binary search
+                    int64_t lo = 0, hi = tilesA - 1;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi + 1) >> 1;
+                        if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
+                    }
+                    mine = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
                 }
-                I = (int)lo;
-                J = __ldg(&jlo[I]) + (int)(w - __ldg(&wprefix[I]));
             }
             for (int l = 0; l < 32; ++l) {
                 if (first + (k0 + l) * stride >= W) break;
-                const int Il = __shfl_sync(0xffffffffu, I, l), Jl = __shfl_sync(0xffffffffu, J, l);
+                const int Il = __shfl_sync(0xffffffffu, mine.x, l), Jl = __shfl_sync(0xffffffffu, mine.y, l);
                 if (lane == 0) {
                     const uint4* gA = bitsA + (size_t)Il * n_chunks * (K4 * TILE);
                     const uint4* gB = bitsB + (size_t)Jl * n_chunks * (K4 * TILE);
                     for (int c = 0; c < n_chunks; ++c, ++it) {
-                        const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+                        const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
                         mbar_wait(&empty_bar[stage], ph ^ 1u);
                         meta[stage] = make_int2(Il, Jl);
                         unsigned char* sa = smem + stage * L::kStageBytes;
@@ -386,16 +453,56 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
     // warp-uniform (broadcast LDS.128), B rows are 32 consecutive 16-byte groups (conflict-free).
     const int tx = lane, ty = warp;
     uint32_t it = 0;
+    unsigned int l2_count = 0;
     for (unsigned long long w = first; w < W; w += stride) {
         int acc[8][4];
+        int2 ij = make_int2(0, 0);
+        bool full_pass = true;
+        if constexpr (TWO_LEVEL) {
+            // ---- level 1: one popc per pair on the 32-bit fold, running minimum only (n_chunks == 1)
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            mbar_wait(&full_bar[stage], ph);
+            const uint4* sA = reinterpret_cast<const uint4*>(smem + stage * L::kStageBytes);
+            const uint4* sB = sA + K4 * TILE;
+            uint32_t fb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t f = 0;
+#pragma unroll
+                for (int k4 = 0; k4 < K4; ++k4) {
+                    const uint4 v = sB[k4 * TILE + tx + 32 * j];
+                    f ^= v.x ^ v.y ^ v.z ^ v.w;
+                }
+                fb[j] = f;
+            }
+            int mn = 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t fa = 0;
+#pragma unroll
+                for (int k4 = 0; k4 < K4; ++k4) {
+                    const uint4 v = sA[k4 * TILE + ty + 16 * i];
+                    fa ^= v.x ^ v.y ^ v.z ^ v.w;
+                }
+                mn = min(mn, min(min(__popc(fa ^ fb[0]), __popc(fa ^ fb[1])),
+                                 min(__popc(fa ^ fb[2]), __popc(fa ^ fb[3]))));
+            }
+            full_pass = __any_sync(0xffffffffu, mn <= threshold);
+            if (!full_pass) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                ++it;
+                continue;
+            }
+            ++l2_count;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0;
-        int2 ij = make_int2(0, 0);
         for (int c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t stage = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
-            mbar_wait(&full_bar[stage], ph);
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            if (!TWO_LEVEL) mbar_wait(&full_bar[stage], ph);
             const uint4* sA = reinterpret_cast<const uint4*>(smem + stage * L::kStageBytes);
             const uint4* sB = sA + K4 * TILE;
 #pragma unroll
@@ -444,6 +551,7 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
             }
         }
     }
+    if (TWO_LEVEL && lane == 0 && l2_count) atomicAdd(&counters->l2_warp_items, (unsigned long long)l2_count);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -523,8 +631,12 @@ __global__ void k_uf_lists(int* __restrict__ parent, const int64_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// K3b: exact verification of the candidates on the CSR rows (two-pointer symmetric difference with
-// early exit at > max_dist — the same merge sklearn's _sparse_manhattan does, on integers) and hook.
+// K3b: exact verification of the candidates on the CSR rows and hook.  A warp takes a batch of 32
+// candidates (one per lane), then works through them one at a time cooperatively: the lanes stride
+// over the shorter row and match each column against a +-max_dist window of the longer row (exact for
+// the <= max_dist decision, see below), a warp sum gives |A n B| and d = |A| + |B| - 2|A n B| — the
+// quantity sklearn's two-pointer merge accumulates (_pairwise_fast.pyx:83-105), on integers.  Hooks and the edge append are then done per
+// lane with one aggregated cursor update per batch.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
@@ -538,43 +650,55 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     for (unsigned long long base = warp_id * 32; base < n; base += n_warps * 32) {
         const unsigned long long c = base + lane;
-        bool is_edge = false;
         int ra = 0, rb = 0;
+        bool keep = false;
         if (c < n) {
             const uint2 pr = cand[c];
             ra = permA[pr.x];
             rb = permB[pr.y];
-            bool keep = true;
+            keep = true;
             if (is_query) keep = (ra != rb) && !(is_query[rb] && ra > rb);
-            if (keep) {
-                int diff = 0;
-                if (!already_exact) {
-                    int64_t ia = indptr[ra], ea = indptr[ra + 1], ib = indptr[rb], eb = indptr[rb + 1];
-                    while (ia < ea && ib < eb) {
-                        int x = indices[ia], y = indices[ib];
-                        if (x == y) { ++ia; ++ib; }
-                        else {
-                            if (++diff > max_dist) break;
-                            if (x < y) ++ia; else ++ib;
+        }
+        unsigned int edge_mask = __ballot_sync(0xffffffffu, keep);
+        if (!already_exact) {
+            unsigned int todo = edge_mask;
+            edge_mask = 0;
+            while (todo) {
+                const int l = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const int a = __shfl_sync(0xffffffffu, ra, l), b = __shfl_sync(0xffffffffu, rb, l);
+                int64_t ia = __ldg(&indptr[a]), la = __ldg(&indptr[a + 1]) - ia;
+                int64_t ib = __ldg(&indptr[b]), lb = __ldg(&indptr[b + 1]) - ib;
+                if (la > lb) { int64_t t = ia; ia = ib; ib = t; t = la; la = lb; lb = t; }
+                int inter = 0;
+                if (lb - la <= (int64_t)max_dist) {  // otherwise d >= |lb - la| > max_dist already
+                    // Both rows ascend.  If |A xor B| <= max_dist, a common column sits at positions that
+                    // differ by at most max_dist in the two rows (at most that many one-sided columns
+                    // precede it), so matching A[k] against B[k-d..k+d] finds every common column; if the
+                    // distance is larger the count can only be too small, i.e. the pair is still rejected.
+                    // No data-dependent addressing: all loads of a sweep are independent and coalesced.
+                    for (int64_t k = lane; k < la; k += 32) {
+                        const int x = __ldg(&indices[ia + k]);
+                        bool hit = false;
+                        for (int o = -max_dist; o <= max_dist; ++o) {
+                            const int64_t j = k + o;
+                            if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
                         }
+                        inter += hit ? 1 : 0;
                     }
-                    if (diff <= max_dist) {
-                        int64_t rest = (ea - ia) + (eb - ib);
-                        diff = rest > (int64_t)max_dist ? max_dist + 1 : diff + (int)rest;
-                    }
+                    inter = __reduce_add_sync(0xffffffffu, inter);
+                    if (la + lb - 2 * (int64_t)inter <= (int64_t)max_dist) edge_mask |= 1u << l;
                 }
-                is_edge = diff <= max_dist;
             }
         }
+        const bool is_edge = (edge_mask >> lane) & 1u;
         if (is_edge) uf_unite(parent, ra, rb);
-        const unsigned int m = __ballot_sync(0xffffffffu, is_edge);
-        if (m) {
+        if (edge_mask) {
             unsigned long long pos0 = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) pos0 = atomicAdd(&counters->n_edges, (unsigned long long)__popc(m));
-            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+            if (lane == 0) pos0 = atomicAdd(&counters->n_edges, (unsigned long long)__popc(edge_mask));
+            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
             if (is_edge && edges) {
-                unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                const unsigned long long pos = pos0 + __popc(edge_mask & ((1u << lane) - 1u));
                 if (pos < edge_cap) edges[pos] = make_uint2((uint32_t)min(ra, rb), (uint32_t)max(ra, rb));
             }
         }

@@ -77,6 +77,9 @@ typedef struct bf_stats {
     int64_t kernel_launches;  /* kernels this library launched in those runs (incl. merges)    */
     double ms_pairs_sum;      /* summed device time of the pair kernel (CUDA events, own stream) */
     double ms_total_sum;      /* summed device time of whole passes                            */
+    /* pair kernel work of the last run on this rank */
+    int64_t l2_warp_items;    /* (warp, tile pair) units that needed the full-width pass (two-level filter) */
+    int64_t popc32_executed;  /* POPC32 lane-ops the pair kernel executed: level 1 + level 2       */
 } bf_stats;
 
 typedef struct bf_ctx bf_ctx;
@@ -92,8 +95,11 @@ int bf_device_count(int* n_out);
  * sees every kernel. */
 int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out);
 void bf_ctx_destroy(bf_ctx* ctx);
-/* Options: "engine" (bf_engine), "sketch_bits" (power of two, 128..4096),
- * "want_edges" (0/1), "cand_capacity" (entries), "blocks_per_sm". */
+/* Options: "engine" (bf_engine), "sketch_bits" (power of two, 128..2048),
+ * "want_edges" (0/1), "cand_capacity" (entries), "blocks_per_sm",
+ * "two_level" (0/1, default 1: 32-bit first-level fold inside the pair kernel for
+ * single-chunk sketches; exact either way), "items_capacity" (entries of the
+ * expanded work list, 0 = automatic). */
 int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
 
 /* ---- async, device-resident API (used by bench.py and the multi-rank host) */

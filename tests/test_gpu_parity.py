@@ -106,6 +106,27 @@ def test_every_sketch_width_is_exact(bits):
         assert np.array_equal(ctx.download_labels(), want)
 
 
+@pytest.mark.parametrize("bits", [128, 256, 512])
+@pytest.mark.parametrize("max_dist", [1, 3])
+def test_two_level_filter_changes_nothing(bits, max_dist):
+    """the 32-bit first-level fold inside the pair kernel is a pure pre-filter: same candidates' edges"""
+    indptr, indices, n_cols = synth.generate(5000, seed=31).csr()
+    outs = []
+    for two_level in (0, 1):
+        with _native.Context(sketch_bits=bits, two_level=two_level, want_edges=1) as ctx:
+            ctx.upload_csr(indptr, indices, n_cols)
+            st = ctx.run_sync(max_dist)
+            outs.append((ctx.download_labels(), *ctx.download_edges(), st.n_candidates))
+            if two_level:
+                assert st.l2_warp_items > 0
+                assert st.popc32_executed == st.pairs_evaluated + st.l2_warp_items * 1024 * (bits // 32)
+            else:
+                assert st.l2_warp_items == 0 and st.popc32_executed == st.pairs_evaluated * (bits // 32)
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][:3], outs[1][:3])) and outs[0][3] == outs[1][3]
+    want, _ = oracle.cluster(indptr, indices, max_dist)
+    assert np.array_equal(outs[1][0], want)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_edge_cases(engine):
     # empty input
