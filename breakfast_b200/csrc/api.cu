@@ -205,10 +205,13 @@ int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t 
     return BF_OK;
 }
 
+#ifndef BF_STAGES_SMALL
+#define BF_STAGES_SMALL 16
+#endif
 int dispatch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
     const bool two = c->ran_two_level;
-    if (c->K4 == 1) return two ? launch_pairs<1, 8, true>(c, A, B, nA, nB, tri) : launch_pairs<1, 8, false>(c, A, B, nA, nB, tri);
-    if (c->K4 == 2) return two ? launch_pairs<2, 8, true>(c, A, B, nA, nB, tri) : launch_pairs<2, 8, false>(c, A, B, nA, nB, tri);
+    if (c->K4 == 1) return two ? launch_pairs<1, BF_STAGES_SMALL, true>(c, A, B, nA, nB, tri) : launch_pairs<1, BF_STAGES_SMALL, false>(c, A, B, nA, nB, tri);
+    if (c->K4 == 2) return two ? launch_pairs<2, BF_STAGES_SMALL, true>(c, A, B, nA, nB, tri) : launch_pairs<2, BF_STAGES_SMALL, false>(c, A, B, nA, nB, tri);
     return two ? launch_pairs<4, 4, true>(c, A, B, nA, nB, tri) : launch_pairs<4, 4, false>(c, A, B, nA, nB, tri);
 }
 

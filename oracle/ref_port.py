@@ -174,12 +174,22 @@ def remap_cached_lists(cache, uniq):
     return kept, new_rows
 
 
-def cluster_table(ids, feats, sep2=" ", max_dist=1, min_cluster_size=2, cache=None, want_cache=False):
-    """ids/filtered profile strings -> (text of clusters.tsv, cache dict or None)."""
+def cluster_table(ids, feats, sep2=" ", max_dist=1, min_cluster_size=2, cache=None, want_cache=False, core="sklearn"):
+    """ids/filtered profile strings -> (text of clusters.tsv, cache dict or None).
+    core="sklearn": the reference's own neighbour search (slow, hours beyond ~1e5 profiles);
+    core="c": oracle.c brute force for the distance part (no cache support) — same results, pinned by
+    tests/test_oracle_golden.py::test_c_oracle_matches_ref_port and test_c_core_matches_goldens."""
     uniq, codes, mult = dedup(feats)
     n = len(uniq)
     if max_dist == 0:
         labels = np.arange(n)
+        lists = None
+    elif core == "c":
+        import oracle
+        assert cache is None and not want_cache
+        indptr, indices, _ = binary_csr(uniq, sep2)
+        labels, _ = oracle.cluster(indptr, indices, max_dist)
+        labels = labels.astype(np.int64)
         lists = None
     else:
         X = count_matrix(uniq, sep2)
@@ -209,11 +219,11 @@ def cluster_table(ids, feats, sep2=" ", max_dist=1, min_cluster_size=2, cache=No
 
 def run_file(path, sep="\t", id_col="accession", clust_col="dna_profile", var_type="covsonar_dna", sep2=" ",
              max_dist=1, min_cluster_size=2, trim_start=264, trim_end=228, reference_length=29903,
-             skip_del=True, skip_ins=True, cache=None, want_cache=False):
+             skip_del=True, skip_ins=True, cache=None, want_cache=False, core="sklearn"):
     """The CLI's five steps (console.py:152-170) on one input table."""
     if var_type not in ("covsonar_dna", "nextclade_dna"):
         trim_start = trim_end = 0
         skip_del = skip_ins = False
     ids, feats = read(path, sep, id_col, clust_col)
     feats = filter_profiles(feats, sep2, var_type, skip_ins, skip_del, trim_start, trim_end, reference_length)
-    return cluster_table(ids, feats, sep2, max_dist, min_cluster_size, cache, want_cache)
+    return cluster_table(ids, feats, sep2, max_dist, min_cluster_size, cache, want_cache, core)

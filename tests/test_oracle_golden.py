@@ -28,6 +28,13 @@ def test_ref_port_plain(case):
     _check(case, case["expected"], text)
 
 
+@pytest.mark.parametrize("case", helpers.cases("plain"), ids=lambda c: c["name"])
+def test_c_core_matches_goldens(case):
+    """the same pipeline with oracle.c doing the distance part (used for 1e5-scale parity tests)"""
+    text, _ = ref_port.run_file(GOLDEN / case["input"], core="c", **_kwargs(case["opts"]))
+    _check(case, case["expected"], text)
+
+
 @pytest.mark.parametrize("case", [c for c in helpers.cases("cached") if "cache_from" in c], ids=lambda c: c["name"])
 def test_ref_port_cached(case):
     first = case["cache_from"]

@@ -14,7 +14,8 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-lib = C.CDLL(str(ROOT / "breakfast_b200" / "libbreakfast_b200.so"))
+import os
+lib = C.CDLL(os.environ.get("BF_LIB", str(ROOT / "breakfast_b200" / "libbreakfast_b200.so")))
 lib.bf_last_error.restype = C.c_char_p
 
 
