@@ -112,11 +112,13 @@ def run_reference_arm(args):
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 50 ms from before the warm-up; only samples that fall inside the timed
+    region are reported (all samples are used, and flagged, if the region was shorter than one poll)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
@@ -130,19 +132,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.05]
+        scope = "timed region"
+        if not inside:
+            inside, scope = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than one 50 ms poll)"
+        sm = sorted(int(r[0]) for r in inside if r and r[0].isdigit())
+        mx = [int(r[1]) for r in inside if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in inside if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,19 +232,21 @@ def main():
     runner = RankRunner(ctx, n, rank, world)
 
     # ---- device-resident leg: `value`
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         runner.step(MAX_DIST)
     st = ctx.sync()
-    clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         runner.step(MAX_DIST)
     ev1.record()
     barrier()
+    clocks.mark_end()
     clock_info = clocks.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     st = ctx.sync()      # counters + per-launch sums over the timed steps
@@ -256,19 +271,41 @@ def main():
             traffic = None
     launches = st.kernel_launches
 
-    # ---- end-to-end leg through the host-buffer C ABI: H2D CSR + pass + D2H labels, every step
-    def e2e_step():
-        ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
-        runner.step(MAX_DIST)
-        _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+    # ---- end-to-end leg through the host-buffer C ABI: every step copies its CSR from pinned host memory
+    # and reads its labels back to the host.
+    #   N = 1: bf_upload_csr_async double-buffers, so the H2D of step k+1 overlaps the pass of step k.
+    #   N > 1: every rank copies 1/N of the column array, the slices are all-gathered over NVLink (NCCL) and
+    #          adopted in place (bf_adopt_csr_device); then the pass, the label all-gather + merge, and D2H.
+    if world == 1:
+        h2d_bytes = int(indptr.nbytes + indices.nbytes)
 
-    for _ in range(3):
-        e2e_step()
+        def e2e_loop(k_steps):
+            ctx.upload_csr_async_ptr(p_indptr.value, p_indices.value, n, n_cols)
+            for k in range(k_steps):
+                runner.step(MAX_DIST)                         # waits for the upload of this step
+                if k + 1 < k_steps:
+                    ctx.upload_csr_async_ptr(p_indptr.value, p_indices.value, n, n_cols)   # overlaps the pass
+                _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+    else:
+        from breakfast_b200.dist import ShardedCsrUploader
+        uploader = ShardedCsrUploader(ctx, indptr, indices, n_cols, rank, world)
+        h2d_bytes = int(uploader.h2d_bytes)
+
+        def e2e_loop(k_steps):
+            uploader.prefetch()
+            for k in range(k_steps):
+                uploader.activate()                           # compute stream waits for this step's CSR
+                if k + 1 < k_steps:
+                    uploader.prefetch()                       # next step's copy + all-gather on the side stream
+                runner.step(MAX_DIST)
+                uploader.release()
+                _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+
+    e2e_loop(3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -309,7 +346,9 @@ def main():
                        "parallelism": f"tile-partition x{world}" if world > 1 else "single GPU"},
             "clocks": clock_info,
             "e2e": {"value": st.pairs_band / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(indptr.nbytes + indices.nbytes), "d2h_bytes_per_step": int(labels_host.nbytes),
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(labels_host.nbytes),
+                    "input_path": "double-buffered async H2D (copy of step k+1 overlaps pass k)" if world == 1 else
+                                  "per-rank 1/N H2D + NCCL all-gather of the CSR over NVLink, double-buffered on a side stream",
                     "labels_sane": ok},
             "gpu_launches": int(launches),
             "roofline": {"kernel": f"k_pairs<K4> ({args.engine}, {st.bits_per_row} bits/row)", "bound": "int_pipe_popc",

@@ -51,7 +51,7 @@ _lib = None
 # every symbol include/breakfast_b200.h declares
 EXPORTS = (
     "bf_abi_version", "bf_last_error", "bf_device_count", "bf_ctx_create", "bf_ctx_destroy", "bf_ctx_set_option",
-    "bf_upload_csr", "bf_run", "bf_labels_to_device", "bf_merge_labels_device", "bf_merge_labels_host",
+    "bf_upload_csr", "bf_upload_csr_async", "bf_adopt_csr_device", "bf_run", "bf_labels_to_device", "bf_merge_labels_device", "bf_merge_labels_host",
     "bf_union_lists", "bf_sync", "bf_download_labels", "bf_edge_count", "bf_download_edges", "bf_cluster_csr",
     "bf_neighbours_csr", "bf_edges_copy", "bf_edges_free", "bf_components", "bf_pinned_alloc", "bf_pinned_free",
     "bf_measure_peak",
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.bf_ctx_destroy.restype = None
     lib.bf_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.bf_upload_csr.argtypes = [vp, vp, vp, i64, i32, vp, i64]
+    lib.bf_upload_csr_async.argtypes = [vp, vp, vp, i64, i32]
+    lib.bf_adopt_csr_device.argtypes = [vp, vp, vp, i64, i32, i64]
     lib.bf_run.argtypes = [vp, i32, i32, i32]
     lib.bf_labels_to_device.argtypes = [vp, vp]
     lib.bf_merge_labels_device.argtypes = [vp, vp, i32]
@@ -188,6 +190,17 @@ class Context:
         """Upload from raw host addresses (e.g. pinned buffers)."""
         self.n_rows = n_rows
         _ck(self._lib.bf_upload_csr(self._h, indptr_ptr, indices_ptr, n_rows, int(n_cols), None, 0))
+
+    def upload_csr_async_ptr(self, indptr_ptr: int, indices_ptr: int, n_rows: int, n_cols: int):
+        """Pinned host buffers -> idle device slot on the context's copy stream (overlaps a running pass)."""
+        self.n_rows = n_rows
+        _ck(self._lib.bf_upload_csr_async(self._h, indptr_ptr, indices_ptr, n_rows, int(n_cols)))
+
+    def adopt_csr_device(self, indptr_dev: int, indices_dev: int, n_rows: int, n_cols: int, nnz: int):
+        """Use caller-owned device memory as the CSR (no copy)."""
+        self.n_rows = n_rows
+        _ck(self._lib.bf_adopt_csr_device(self._h, C.c_void_p(indptr_dev), C.c_void_p(indices_dev), n_rows,
+                                          int(n_cols), int(nnz)))
 
     def run(self, max_dist: int, rank: int = 0, world: int = 1):
         _ck(self._lib.bf_run(self._h, int(max_dist), int(rank), int(world)))

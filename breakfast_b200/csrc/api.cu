@@ -108,7 +108,17 @@ struct bf_ctx {
     bool ran_two_level = false;
     float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
 
-    DevBuf indptr, indices, query_rows, is_query;
+    // CSR on the device: two owned slots (async uploads fill the idle one while a pass runs on the
+    // other) or caller-owned memory (bf_adopt_csr_device); d_indptr/d_indices is what kernels read
+    DevBuf indptr[2], indices[2], query_rows, is_query;
+    const int64_t* d_indptr = nullptr;
+    const int32_t* d_indices = nullptr;
+    int cur = 0, pending = -1;
+    int64_t pend_rows = 0, pend_nnz = 0;
+    int32_t pend_cols = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
+    bool slot_used[2] = {false, false};
     DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
     DevBuf bitsA, bitsB, jlo, wprefix, nwork, items, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
@@ -141,7 +151,7 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
     TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
     uint32_t* max_key = c->sort_max.as<uint32_t>() + side;
     CK(cudaMemsetAsync(max_key, 0, sizeof(uint32_t), c->stream));
-    k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(), rows_dev, n,
+    k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_indptr, rows_dev, n,
                                                           keys[0].as<uint32_t>(), vals[0].as<int32_t>(), max_key);
     CKLC(c);
     for (int pass = 0; pass < 2; ++pass) {
@@ -169,14 +179,14 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
         int log2m = 0;
         while ((1 << log2m) < c->sketch_bits) ++log2m;
         const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
-        k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
+        k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices,
                                                                  perm_dev, n, log2m, c->n_chunks, c->K4,
                                                                  bits.as<uint32_t>());
         CKLC(c);
     } else {
         CK(cudaMemsetAsync(bits.p, 0, bytes, c->stream));
-        k_pack_full<<<grid_for(n * 32, 256), 256, 0, c->stream>>>(c->indptr.as<int64_t>(),
-                                                                  c->indices.as<int32_t>(), perm_dev, n,
+        k_pack_full<<<grid_for(n * 32, 256), 256, 0, c->stream>>>(c->d_indptr,
+                                                                  c->d_indices, perm_dev, n,
                                                                   c->n_chunks, c->K4, bits.as<uint32_t>());
         CKLC(c);
     }
@@ -276,6 +286,10 @@ int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out) {
     }
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_aux[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_upload_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_upload_done);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_slot_free[i], cudaEventDisableTiming);
     for (int i = 0; i < bf_ctx::kRing && e == cudaSuccess; ++i)
         for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&c->ring[i][j]);
     if (e == cudaSuccess) {
@@ -299,7 +313,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->indptr, &c->indices, &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
+    DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
                       &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->jlo, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
@@ -307,6 +321,10 @@ void bf_ctx_destroy(bf_ctx* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_aux) if (e) cudaEventDestroy(e);
     for (auto& r : c->ring) for (auto& e : r) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_upload_start) cudaEventDestroy(c->ev_upload_start);
+    if (c->ev_upload_done) cudaEventDestroy(c->ev_upload_done);
+    for (auto& e : c->ev_slot_free) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -365,16 +383,24 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
     c->uploaded = false;
     c->ran = false;
     CK(cudaEventRecord(c->ev_aux[0], c->stream));
-    TRY(c->indptr.ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
-    TRY(c->indices.ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    if (c->pending >= 0) {  // an async upload is still in flight: let it land before reusing state
+        CK(cudaStreamSynchronize(c->copy_stream));
+        c->pending = -1;
+    }
+    DevBuf& dip = c->indptr[c->cur];
+    DevBuf& dix = c->indices[c->cur];
+    TRY(dip.ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
+    TRY(dix.ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     if (n_rows > 0) {
-        CK(cudaMemcpyAsync(c->indptr.p, indptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-        if (nnz > 0) CK(cudaMemcpyAsync(c->indices.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dip.p, indptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        if (nnz > 0) CK(cudaMemcpyAsync(dix.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     } else {
         int64_t zero = 0;
-        CK(cudaMemcpyAsync(c->indptr.p, &zero, sizeof zero, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dip.p, &zero, sizeof zero, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
+    c->d_indptr = dip.as<int64_t>();
+    c->d_indices = dix.as<int32_t>();
     c->has_query = query_rows != nullptr;
     c->n_query = c->has_query ? n_query : n_rows;
     if (c->has_query) {
@@ -398,12 +424,70 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
     return BF_OK;
 }
 
+int bf_upload_csr_async(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (n_rows <= 0 || n_cols < 0 || n_rows > (int64_t)2147483647 - 2 * TILE) return fail(BF_ERR_INVALID, "n_rows/n_cols out of range");
+    if (!indptr) return fail(BF_ERR_INVALID, "indptr is null");
+    if (indptr[0] != 0) return fail(BF_ERR_INVALID, "indptr[0] must be 0");
+    for (int64_t i = 0; i < n_rows; ++i)
+        if (indptr[i + 1] < indptr[i]) return fail(BF_ERR_INVALID, "indptr must be non-decreasing");
+    const int64_t nnz = indptr[n_rows];
+    if (nnz > 0 && !indices) return fail(BF_ERR_INVALID, "indices is null");
+    TRY(set_device(c));
+    if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is already pending; call bf_run first");
+    const int slot = (c->d_indptr == c->indptr[c->cur].as<int64_t>() && c->d_indptr) ? c->cur ^ 1 : c->cur;
+    TRY(c->indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
+    TRY(c->indices[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    if (c->slot_used[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_free[slot], 0));
+    CK(cudaEventRecord(c->ev_upload_start, c->copy_stream));
+    CK(cudaMemcpyAsync(c->indptr[slot].p, indptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (nnz > 0) CK(cudaMemcpyAsync(c->indices[slot].p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_upload_done, c->copy_stream));
+    c->pending = slot;
+    c->pend_rows = n_rows;
+    c->pend_cols = n_cols;
+    c->pend_nnz = nnz;
+    c->uploaded = true;
+    return BF_OK;
+}
+
+int bf_adopt_csr_device(bf_ctx* c, const void* indptr_device, const void* indices_device, int64_t n_rows,
+                        int32_t n_cols, int64_t nnz) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (n_rows < 0 || n_cols < 0 || nnz < 0 || n_rows > (int64_t)2147483647 - 2 * TILE) return fail(BF_ERR_INVALID, "size out of range");
+    if (!indptr_device || (nnz > 0 && !indices_device)) return fail(BF_ERR_INVALID, "null device pointer");
+    if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is pending");
+    c->d_indptr = static_cast<const int64_t*>(indptr_device);
+    c->d_indices = static_cast<const int32_t*>(indices_device);
+    c->n_rows = c->n_query = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->has_query = false;
+    c->uploaded = true;
+    c->ran = false;
+    c->ms_h2d = 0;
+    return BF_OK;
+}
+
 int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     if (!c) return fail(BF_ERR_INVALID, "ctx is null");
     if (!c->uploaded) return fail(BF_ERR_STATE, "bf_run before bf_upload_csr");
     if (max_dist < 0) return fail(BF_ERR_INVALID, "max_dist must be >= 0");
     if (world < 1 || rank < 0 || rank >= world) return fail(BF_ERR_INVALID, "need 0 <= rank < world");
     TRY(set_device(c));
+    if (c->pending >= 0) {
+        // the CSR of this pass was uploaded asynchronously into the idle slot: order after the copy
+        CK(cudaStreamWaitEvent(c->stream, c->ev_upload_done, 0));
+        c->cur = c->pending;
+        c->pending = -1;
+        c->d_indptr = c->indptr[c->cur].as<int64_t>();
+        c->d_indices = c->indices[c->cur].as<int32_t>();
+        c->n_rows = c->n_query = c->pend_rows;
+        c->n_cols = c->pend_cols;
+        c->nnz = c->pend_nnz;
+        c->has_query = false;
+        c->ms_h2d = -1.f;  // resolved in bf_sync from the copy-stream events
+    }
     c->max_dist = max_dist;
     c->rank = rank;
     c->world = world;
@@ -506,7 +590,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         // ---- K3b: verify + hook
         k_verify_unite<<<c->num_sms * 8, 256, 0, c->stream>>>(
             c->cand.as<uint2>(), c->cand_cap_used, valsA[0].as<int32_t>(), c->valsB[0].as<int32_t>(),
-            c->indptr.as<int64_t>(), c->indices.as<int32_t>(), max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
+            c->d_indptr, c->d_indices, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
             c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
             c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
         CKLC(c);
@@ -516,6 +600,10 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     TRY(finish_labels(c));
     CK(cudaEventRecord(c->ev[6], c->stream));
     CK(cudaEventRecord(ring[3], c->stream));
+    if (c->d_indptr == c->indptr[c->cur].as<int64_t>()) {
+        CK(cudaEventRecord(c->ev_slot_free[c->cur], c->stream));  // the idle slot may be refilled after this
+        c->slot_used[c->cur] = true;
+    }
     ++c->runs_since_sync;
     c->ran = true;
     return BF_OK;
@@ -626,6 +714,14 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
                                                    : st->pairs_evaluated * words;
         }
         float ms = 0;
+        if (c->ms_h2d < 0) {
+            // copy-stream events may already belong to the next (still running) async upload
+            c->ms_h2d = 0;
+            if (cudaEventQuery(c->ev_upload_done) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, c->ev_upload_start, c->ev_upload_done) == cudaSuccess)
+                c->ms_h2d = ms;
+            (void)cudaGetLastError();
+        }
         st->ms_h2d = c->ms_h2d;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); st->ms_sort = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); st->ms_pack = ms;

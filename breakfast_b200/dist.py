@@ -50,3 +50,71 @@ class RankRunner:
             self.ctx.labels_to_device(self.local.data_ptr())
             dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
             self.ctx.merge_labels_device(self.gathered.data_ptr(), self.world)
+
+
+class ShardedCsrUploader:
+    """End-to-end input path for N ranks: every rank copies only its 1/N slice of the column array
+    from pinned host memory (the PCIe links work in parallel), the slices are all-gathered over
+    NVLink, and the context adopts the gathered device CSR without another copy.
+
+    Two device slots and a side stream: `prefetch()` enqueues copy + all-gather of the NEXT batch on
+    the side stream while the current pass runs; `activate()` makes the compute stream wait for it and
+    hands the slot to the context; `release()` (after the pass is enqueued) marks when the slot may be
+    refilled.  Call order per step: activate, prefetch (next), run, release — the CSR all-gather is
+    issued before the step's label all-gather so NCCL does not serialise it behind the pass."""
+
+    def __init__(self, ctx, indptr, indices, n_cols: int, rank: int, world: int, group=None):
+        import torch
+        self.ctx, self.n_cols, self.rank, self.world, self.group = ctx, int(n_cols), rank, world, group
+        self.n_rows, self.nnz = len(indptr) - 1, int(indices.size)
+        chunk = max(1, -(-self.nnz // world))
+        lo, hi = min(rank * chunk, self.nnz), min((rank + 1) * chunk, self.nnz)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.h_indptr = torch.from_numpy(indptr).pin_memory()
+        self.h_shard = torch.zeros(chunk, dtype=torch.int32).pin_memory()
+        self.h_shard[: hi - lo] = torch.from_numpy(indices[lo:hi])
+        self.d_indptr = [torch.empty(self.n_rows + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.d_shard = [torch.empty(chunk, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.d_full = [torch.empty(world * chunk, dtype=torch.int32, device=dev) if world > 1 else None for _ in range(2)]
+        self.h2d_bytes = self.h_indptr.numel() * 8 + chunk * 4
+        self.main = torch.cuda.current_stream()
+        self.side = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+        self.next_slot, self.active = 0, None
+
+    def prefetch(self):
+        """copy + all-gather the next batch into the idle slot, on the side stream"""
+        import torch
+        import torch.distributed as dist
+        s = self.next_slot
+        with torch.cuda.stream(self.side):
+            if self.free[s] is not None:
+                self.side.wait_event(self.free[s])
+            self.d_indptr[s].copy_(self.h_indptr, non_blocking=True)
+            self.d_shard[s].copy_(self.h_shard, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.d_full[s], self.d_shard[s], group=self.group)
+            self.ready[s].record(self.side)
+        self.pending = s
+        self.next_slot = s ^ 1
+
+    def activate(self):
+        """the compute stream waits for the prefetched batch; the context adopts it (no copy)"""
+        s = self.pending
+        self.main.wait_event(self.ready[s])
+        full = self.d_full[s] if self.world > 1 else self.d_shard[s]
+        self.ctx.adopt_csr_device(self.d_indptr[s].data_ptr(), full.data_ptr(), self.n_rows, self.n_cols, self.nnz)
+        self.active = s
+
+    def release(self):
+        """call after the pass on the active slot has been enqueued"""
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.free[self.active] = ev
+
+    def upload(self):
+        """unpipelined convenience: prefetch + activate"""
+        self.prefetch()
+        self.activate()

@@ -109,6 +109,17 @@ int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
 int bf_upload_csr(bf_ctx* ctx, const int64_t* indptr, const int32_t* indices,
                   int64_t n_rows, int32_t n_cols,
                   const int32_t* query_rows, int64_t n_query);
+/* Pipelined variant for callers that stream batches: the host buffers must be page-locked
+ * (bf_pinned_alloc) and stay valid until the next bf_sync/bf_download_labels.  The copy runs on the
+ * context's own copy stream into the idle one of two device slots, so it overlaps the pass that is
+ * still running; the next bf_run waits for it and switches slots. */
+int bf_upload_csr_async(bf_ctx* ctx, const int64_t* indptr, const int32_t* indices,
+                        int64_t n_rows, int32_t n_cols);
+/* Use a CSR that already lives in device memory owned by the caller (e.g. row shards that the ranks
+ * uploaded in parallel and all-gathered over NVLink with torch.distributed).  Not copied; the caller
+ * keeps it alive and orders its producers before bf_run on the context's stream. */
+int bf_adopt_csr_device(bf_ctx* ctx, const void* indptr_device, const void* indices_device,
+                        int64_t n_rows, int32_t n_cols, int64_t nnz);
 /* Enqueue one pass of the hot path on the uploaded rows for this rank's share of
  * the band tiles: cardinality sort -> bit-pack -> tile schedule -> XOR/POPC pair
  * kernel -> exact verify -> union-find -> labels (device).  Nothing is copied to

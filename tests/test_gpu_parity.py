@@ -292,6 +292,46 @@ def test_determinism_and_pinned_memory():
     assert np.array_equal(outs[0][0], want)
 
 
+def test_async_double_buffered_upload_and_adopted_device_csr():
+    """bf_upload_csr_async alternates two device slots (different batches back to back give each its
+    own answer) and bf_adopt_csr_device runs on caller-owned device memory."""
+    torch = pytest.importorskip("torch")
+    batches = [synth.generate(n, seed=s).csr() for n, s in ((9000, 1), (7000, 2), (9000, 3))]
+    wants = [oracle.cluster(ip, ix, 1)[0] for ip, ix, _ in batches]
+    lib = _native.load()
+    pinned = []
+    for ip, ix, _ in batches:
+        a, b = C.c_void_p(), C.c_void_p()
+        assert lib.bf_pinned_alloc(ip.nbytes, C.byref(a)) == 0 and lib.bf_pinned_alloc(ix.nbytes, C.byref(b)) == 0
+        C.memmove(a, ip.ctypes.data, ip.nbytes)
+        C.memmove(b, ix.ctypes.data, ix.nbytes)
+        pinned.append((a, b))
+    with _native.Context() as ctx:
+        ctx.upload_csr_async_ptr(pinned[0][0].value, pinned[0][1].value, len(batches[0][0]) - 1, batches[0][2])
+        for k in range(6):
+            cur = k % 3
+            ctx.run(1)
+            nxt = (k + 1) % 3
+            ctx.upload_csr_async_ptr(pinned[nxt][0].value, pinned[nxt][1].value, len(batches[nxt][0]) - 1, batches[nxt][2])
+            ctx.n_rows = len(batches[cur][0]) - 1
+            assert np.array_equal(ctx.download_labels(), wants[cur]), k
+        with pytest.raises(_native.NativeError):        # one pending upload at a time
+            ctx.upload_csr_async_ptr(pinned[0][0].value, pinned[0][1].value, len(batches[0][0]) - 1, batches[0][2])
+        ctx.run(1)
+        ctx.sync()
+    for a, b in pinned:
+        lib.bf_pinned_free(a)
+        lib.bf_pinned_free(b)
+    ip, ix, nc = batches[1]
+    ts = torch.cuda.Stream()
+    with torch.cuda.stream(ts):
+        d_ip, d_ix = torch.from_numpy(ip).cuda(), torch.from_numpy(ix).cuda()
+        with _native.Context(stream=ts.cuda_stream) as ctx:
+            ctx.adopt_csr_device(d_ip.data_ptr(), d_ix.data_ptr(), len(ip) - 1, nc, ix.size)
+            ctx.run_sync(1)
+            assert np.array_equal(ctx.download_labels(), wants[1])
+
+
 def test_measured_pipe_peaks_are_plausible():
     assert _native.measure_peak("popc32") > 1000.0
     assert _native.measure_peak("lop3") > _native.measure_peak("popc32")
