@@ -178,10 +178,15 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
     if (c->engine == BF_ENGINE_SKETCH) {
         int log2m = 0;
         while ((1 << log2m) < c->sketch_bits) ++log2m;
-        const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
-        k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices,
-                                                                 perm_dev, n, log2m, c->n_chunks, c->K4,
-                                                                 bits.as<uint32_t>());
+        if (c->sketch_bits == 128) {
+            k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>());
+        } else if (c->sketch_bits == 256) {
+            k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>());
+        } else {
+            const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
+            k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
+                                                                     c->n_chunks, c->K4, bits.as<uint32_t>());
+        }
         CKLC(c);
     } else {
         CK(cudaMemsetAsync(bits.p, 0, bytes, c->stream));
@@ -588,7 +593,11 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(ring[2], c->stream));
     if (active) {
         // ---- K3b: verify + hook
-        k_verify_unite<<<c->num_sms * 8, 256, 0, c->stream>>>(
+        auto verify = k_verify_unite<0>;   // window = max_dist: a wider compile-time window would still be exact
+        if (max_dist == 1) verify = k_verify_unite<1>;
+        else if (max_dist == 2) verify = k_verify_unite<2>;
+        else if (max_dist == 3) verify = k_verify_unite<3>;
+        verify<<<c->num_sms * 8, 256, 0, c->stream>>>(
             c->cand.as<uint2>(), c->cand_cap_used, valsA[0].as<int32_t>(), c->valsB[0].as<int32_t>(),
             c->d_indptr, c->d_indices, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
             c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),

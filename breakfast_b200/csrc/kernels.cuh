@@ -28,7 +28,7 @@ namespace bf {
 
 constexpr int TILE = 128;              // rows per tile (both operands)
 constexpr uint32_t KEY_CLAMP = 65535;  // cardinality sort key is clamped (1-Lipschitz, band test stays sound)
-constexpr int SORT_ITEMS = 1024;       // rows per block in the radix passes
+constexpr int SORT_ITEMS = 2048;       // rows per block in the radix passes
 constexpr int PAIR_CONSUMER_WARPS = 16;
 constexpr int PAIR_THREADS = (PAIR_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 
@@ -62,53 +62,90 @@ __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* _
     if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(max_key, k);
 }
 
+// One radix pass = k_sort_hist -> k_exclusive_scan -> k_sort_scatter.  A block owns SORT_ITEMS
+// consecutive rows, warp w of it the w-th eighth; every warp keeps a private 256-bin histogram in
+// shared memory (no atomics: __match_any_sync groups equal digits, the group leader adds the group
+// size), so ranks are reproducible and the pass is stable.
 // counts[digit * nblocks + block] = number of rows of `block` whose digit == digit
+constexpr int SORT_WARPS = 8;
+constexpr int SORT_PER_WARP = SORT_ITEMS / SORT_WARPS;
+
+__device__ __forceinline__ void sort_warp_count(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t wbase,
+                                                uint32_t* __restrict__ whist, int lane) {
+    for (int r = 0; r < SORT_PER_WARP; r += 32) {
+        const int64_t i = wbase + r + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;  // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
                                                    uint32_t* __restrict__ counts, int nblocks,
                                                    const uint32_t* __restrict__ max_key) {
     if ((*max_key >> shift) == 0) return;  // every digit of this pass is 0: identity pass
-    __shared__ uint16_t dig[SORT_ITEMS];
-    const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
-    const int m = (int)min((int64_t)SORT_ITEMS, n - base);
-    for (int i = threadIdx.x; i < m; i += 256) dig[i] = (uint16_t)((keys[base + i] >> shift) & 255u);
+    __shared__ uint32_t whist[SORT_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
     __syncthreads();
-    const uint16_t d = (uint16_t)threadIdx.x;
+    sort_warp_count(keys, n, shift, (int64_t)blockIdx.x * SORT_ITEMS + warp * SORT_PER_WARP, whist[warp], lane);
+    __syncthreads();
     uint32_t c = 0;
-    for (int i = 0; i < m; ++i) c += (dig[i] == d);
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) c += whist[w][threadIdx.x];
     counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = c;
 }
 
-// stable scatter: thread d walks the block's rows in order and places those with digit d
 __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys,
                                                       const int32_t* __restrict__ vals, int64_t n, int shift,
                                                       const uint32_t* __restrict__ offsets, int nblocks,
                                                       uint32_t* __restrict__ keys_out,
                                                       int32_t* __restrict__ vals_out,
                                                       const uint32_t* __restrict__ max_key) {
-    __shared__ uint32_t sk[SORT_ITEMS];
-    __shared__ int32_t sv[SORT_ITEMS];
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
-    const int m = (int)min((int64_t)SORT_ITEMS, n - base);
     if ((*max_key >> shift) == 0) {  // identity pass: plain copy
+        const int m = (int)min((int64_t)SORT_ITEMS, n - base);
         for (int i = threadIdx.x; i < m; i += 256) {
             keys_out[base + i] = keys[base + i];
             vals_out[base + i] = vals[base + i];
         }
         return;
     }
-    for (int i = threadIdx.x; i < m; i += 256) {
-        sk[i] = keys[base + i];
-        sv[i] = vals[base + i];
+    __shared__ uint32_t whist[SORT_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t wbase = base + warp * SORT_PER_WARP;
+    sort_warp_count(keys, n, shift, wbase, whist[warp], lane);
+    __syncthreads();
+    {   // digit d: global start of the block + exclusive prefix over the warps of the block
+        uint32_t run = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t c = whist[w][threadIdx.x];
+            whist[w][threadIdx.x] = run;
+            run += c;
+        }
     }
     __syncthreads();
-    const uint32_t d = threadIdx.x;
-    uint32_t pos = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
-    for (int i = 0; i < m; ++i) {
-        uint32_t k = sk[i];
-        if (((k >> shift) & 255u) == d) {
+    uint32_t* wpos = whist[warp];
+    for (int r = 0; r < SORT_PER_WARP; r += 32) {
+        const int64_t i = wbase + r + lane;
+        const bool valid = i < n;
+        const uint32_t k = valid ? keys[i] : 0u;
+        const uint32_t d = valid ? ((k >> shift) & 255u) : 256u + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned below = peers & ((1u << lane) - 1u);
+        uint32_t pos = 0;
+        if (valid) pos = wpos[d] + __popc(below);
+        __syncwarp();
+        if (valid && below == 0) wpos[d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
             keys_out[pos] = k;
-            vals_out[pos] = sv[i];
-            ++pos;
+            vals_out[pos] = vals[i];
         }
     }
 }
@@ -279,6 +316,49 @@ __global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__
     uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)tile * words_per_tile);
     const uint4* src = reinterpret_cast<const uint4*>(tile_words);
     for (int i = threadIdx.x; i < words_per_tile / 4; i += 256) dst[i] = src[i];
+}
+
+// SKETCH, m = 32*WORDS <= 256 bits: no shared memory and no atomics.  A warp folds one row at a time:
+// every lane XORs its columns' bits into WORDS registers, redux.sync.xor combines the lanes, lane 0
+// stores the row's 16-byte groups.  HBM-bound: reads 4*nnz + 12*N bytes, writes N*m/8 bytes.
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restrict__ indptr,
+                                                         const int32_t* __restrict__ indices,
+                                                         const int32_t* __restrict__ perm, int64_t n, int log2m,
+                                                         uint32_t* __restrict__ bits) {
+    constexpr int K4 = WORDS / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    int64_t my_b = 0, my_e = 0;
+    if (lane < TILE / 8) {
+        const int64_t p = tile * TILE + warp + 8 * lane;
+        if (p < n) {
+            const int32_t r = perm[p];
+            my_b = indptr[r];
+            my_e = indptr[r + 1];
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(bits) + (size_t)tile * (K4 * TILE);
+#pragma unroll 4
+    for (int k = 0; k < TILE / 8; ++k) {
+        const int64_t b = __shfl_sync(0xffffffffu, my_b, k), e = __shfl_sync(0xffffffffu, my_e, k);
+        uint32_t w[WORDS];
+#pragma unroll
+        for (int t = 0; t < WORDS; ++t) w[t] = 0u;
+        for (int64_t q = b + lane; q < e; q += 32) {
+            const uint32_t h = fold_hash((uint32_t)__ldg(&indices[q]), log2m);
+            const uint32_t bit = 1u << (h & 31), word = h >> 5;
+#pragma unroll
+            for (int t = 0; t < WORDS; ++t) w[t] ^= (word == (uint32_t)t) ? bit : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < WORDS; ++t) w[t] = __reduce_xor_sync(0xffffffffu, w[t]);
+        if (lane == 0) {
+            const int row = warp + 8 * k;  // rows past n stay all-zero (never emitted: index check in k_pairs)
+#pragma unroll
+            for (int g = 0; g < K4; ++g) dst[g * TILE + row] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+        }
+    }
 }
 
 // FULL: bit matrix pre-zeroed by the host (cudaMemsetAsync); one warp per row sets its bits.
@@ -638,6 +718,7 @@ __global__ void k_uf_lists(int* __restrict__ parent, const int64_t* __restrict__
 // quantity sklearn's two-pointer merge accumulates (_pairwise_fast.pyx:83-105), on integers.  Hooks and the edge append are then done per
 // lane with one aggregated cursor update per batch.
 // ------------------------------------------------------------------------------------------
+template <int DWIN>
 __global__ void __launch_bounds__(256)
 k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
                const int32_t* __restrict__ permB, const int64_t* __restrict__ indptr,
@@ -661,15 +742,22 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
         }
         unsigned int edge_mask = __ballot_sync(0xffffffffu, keep);
         if (!already_exact) {
+            // row extents of all 32 candidates at once (one latency for the batch, not one per candidate)
+            int64_t my_ia = 0, my_la = 0, my_ib = 0, my_lb = 0;
+            if (keep) {
+                my_ia = __ldg(&indptr[ra]);
+                my_la = __ldg(&indptr[ra + 1]) - my_ia;
+                my_ib = __ldg(&indptr[rb]);
+                my_lb = __ldg(&indptr[rb + 1]) - my_ib;
+                if (my_la > my_lb) { int64_t t = my_ia; my_ia = my_ib; my_ib = t; t = my_la; my_la = my_lb; my_lb = t; }
+            }
             unsigned int todo = edge_mask;
             edge_mask = 0;
             while (todo) {
                 const int l = __ffs((int)todo) - 1;
                 todo &= todo - 1;
-                const int a = __shfl_sync(0xffffffffu, ra, l), b = __shfl_sync(0xffffffffu, rb, l);
-                int64_t ia = __ldg(&indptr[a]), la = __ldg(&indptr[a + 1]) - ia;
-                int64_t ib = __ldg(&indptr[b]), lb = __ldg(&indptr[b + 1]) - ib;
-                if (la > lb) { int64_t t = ia; ia = ib; ib = t; t = la; la = lb; lb = t; }
+                const int64_t ia = __shfl_sync(0xffffffffu, my_ia, l), la = __shfl_sync(0xffffffffu, my_la, l);
+                const int64_t ib = __shfl_sync(0xffffffffu, my_ib, l), lb = __shfl_sync(0xffffffffu, my_lb, l);
                 int inter = 0;
                 if (lb - la <= (int64_t)max_dist) {  // otherwise d >= |lb - la| > max_dist already
                     // Both rows ascend.  If |A xor B| <= max_dist, a common column sits at positions that
@@ -677,14 +765,30 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                     // precede it), so matching A[k] against B[k-d..k+d] finds every common column; if the
                     // distance is larger the count can only be too small, i.e. the pair is still rejected.
                     // No data-dependent addressing: all loads of a sweep are independent and coalesced.
-                    for (int64_t k = lane; k < la; k += 32) {
-                        const int x = __ldg(&indices[ia + k]);
-                        bool hit = false;
-                        for (int o = -max_dist; o <= max_dist; ++o) {
-                            const int64_t j = k + o;
-                            if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
+                    if constexpr (DWIN > 0) {
+                        // compile-time window: every load of a sweep is independent and the sweeps are
+                        // unrolled, so a candidate costs about one memory round trip
+#pragma unroll 4
+                        for (int64_t k = lane; k < la; k += 32) {
+                            const int x = __ldg(&indices[ia + k]);
+                            bool hit = false;
+#pragma unroll
+                            for (int o = -DWIN; o <= DWIN; ++o) {
+                                const int64_t j = k + o;
+                                if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
+                            }
+                            inter += hit ? 1 : 0;
                         }
-                        inter += hit ? 1 : 0;
+                    } else {
+                        for (int64_t k = lane; k < la; k += 32) {
+                            const int x = __ldg(&indices[ia + k]);
+                            bool hit = false;
+                            for (int o = -max_dist; o <= max_dist; ++o) {
+                                const int64_t j = k + o;
+                                if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
+                            }
+                            inter += hit ? 1 : 0;
+                        }
                     }
                     inter = __reduce_add_sync(0xffffffffu, inter);
                     if (la + lb - 2 * (int64_t)inter <= (int64_t)max_dist) edge_mask |= 1u << l;
