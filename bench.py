@@ -260,13 +260,39 @@ def main():
     # per-launch duration of the dominant kernel over the timed region (CUDA events on the launching stream)
     runs = max(1, min(st.runs_since_sync, 128))
     ms_pairs = st.ms_pairs_sum / runs
-    popc_per_launch = st.popc32_executed   # level-1 fold (1 per pair) + full-width pass of the surviving warps
-    achieved = popc_per_launch / (ms_pairs * 1e-3) / 1e9
+    two_kernel = args.engine == "sketch" and args.two_level and st.bits_per_row in (128, 256)
+    if two_kernel:
+        # dominant kernel = k_pairs_l1<T>.  Per evaluated pair it executes:
+        #   T = max_dist in {1,2}: 1 XOR + T/2 AND + 1/2 min on the ALU pipe, 1/2 POPC on the XU pipe, T/2 IMAD (FMA)
+        #   otherwise            : 1 XOR + 1/2 min on the ALU pipe, 1 POPC on the XU pipe
+        hybrid = MAX_DIST in (1, 2)
+        alu_per_pair = 1.0 + (MAX_DIST / 2.0 if hybrid else 0.0) + 0.5
+        popc_per_pair = 0.5 if hybrid else 1.0
+        ms_kernel = st.ms_l1_sum / runs
+        kernel_name = f"k_pairs_l1<{MAX_DIST if hybrid else 0}> (32-bit fold level 1 of {st.bits_per_row}-bit sketches)"
+        alu_rate = st.pairs_evaluated * alu_per_pair / (ms_kernel * 1e-3) / 1e9
+        xu_rate = st.pairs_evaluated * popc_per_pair / (ms_kernel * 1e-3) / 1e9
+        alu_frac, xu_frac = alu_rate / peaks["lop3"], xu_rate / peaks["popc32"]
+        if alu_frac >= xu_frac:
+            bound, achieved, peak, unit_r = "int_pipe_alu", alu_rate, peaks["lop3"], "G lane-op/s (LOP3-class)"
+        else:
+            bound, achieved, peak, unit_r = "int_pipe_popc", xu_rate, peaks["popc32"], "GPOPC32/s"
+        ops_per_launch = int(st.pairs_evaluated * (alu_per_pair if bound == "int_pipe_alu" else popc_per_pair))
+        extra = {"alu_frac": alu_frac, "xu_frac": xu_frac, "alu_ops_per_pair": alu_per_pair, "popc_per_pair": popc_per_pair,
+                 "level2_units": st.l2_warp_items, "ms_level2": (st.ms_pairs_sum - st.ms_l1_sum) / runs}
+    else:
+        ms_kernel = ms_pairs
+        kernel_name = f"k_pairs<K4> ({args.engine}, {st.bits_per_row} bits/row)"
+        bound, unit_r, peak = "int_pipe_popc", "GPOPC32/s", peaks["popc32"]
+        ops_per_launch = int(st.popc32_executed)
+        achieved = ops_per_launch / (ms_kernel * 1e-3) / 1e9
+        extra = {}
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(f"k_pairs_{args.engine}_{st.bits_per_row}_n{n}_w{world}")
+            key = ("k_pairs_l1" if two_kernel else "k_pairs") + f"_{args.engine}_{st.bits_per_row}_n{n}_w{world}"
+            traffic = json.loads(tf.read_text()).get(key)
         except Exception:
             traffic = None
     launches = st.kernel_launches
@@ -351,12 +377,12 @@ def main():
                                   "per-rank 1/N H2D + NCCL all-gather of the CSR over NVLink, double-buffered on a side stream",
                     "labels_sane": ok},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": f"k_pairs<K4> ({args.engine}, {st.bits_per_row} bits/row)", "bound": "int_pipe_popc",
-                         "achieved": achieved, "peak": peaks["popc32"], "unit": "GPOPC32/s", "frac": achieved / peaks["popc32"],
-                         "traffic": traffic, "ms_per_launch": ms_pairs, "popc32_per_launch": int(popc_per_launch),
-                         "peak_source": "bf_measure_peak('popc32') measured in this process; MEASURED_PEAKS.json holds only "
-                                        "HBM and bf16 peaks and this kernel is bound by the POPC (XU) pipe",
-                         "kernel_share_of_step": ms_pairs / (st.ms_total_sum / runs) if st.ms_total_sum else None},
+            "roofline": dict({"kernel": kernel_name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit_r,
+                              "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms_kernel,
+                              "ops_per_launch": ops_per_launch,
+                              "peak_source": "bf_measure_peak('lop3'/'popc32') measured in this process; MEASURED_PEAKS.json "
+                                             "holds only HBM and bf16 peaks and this kernel is bound by the integer pipes",
+                              "kernel_share_of_step": ms_kernel / (st.ms_total_sum / runs) if st.ms_total_sum else None}, **extra),
             "cpu_baseline": cpu,
             "phases_ms": {k: getattr(st, k) for k in ("ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge")},
         }

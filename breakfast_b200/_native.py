@@ -40,7 +40,8 @@ class Stats(C.Structure):
     _fields_ = ([(n, C.c_int64) for n in _int_fields] + [(n, C.c_double) for n in _dbl_fields]
                 + [("runs_since_sync", C.c_int64), ("kernel_launches", C.c_int64),
                    ("ms_pairs_sum", C.c_double), ("ms_total_sum", C.c_double),
-                   ("l2_warp_items", C.c_int64), ("popc32_executed", C.c_int64)])
+                   ("l2_warp_items", C.c_int64), ("popc32_executed", C.c_int64),
+                   ("ms_l1_sum", C.c_double)])
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -94,6 +94,7 @@ struct bf_ctx {
     int blocks_per_sm = 0;      // 0 = occupancy
     int two_level = 1;
     int64_t items_capacity = 0;  // 0 = auto
+    int64_t units_capacity = 0;  // 0 = auto (level-2 queue)
 
     // problem
     bool uploaded = false, ran = false, has_query = false;
@@ -105,7 +106,8 @@ struct bf_ctx {
     int K4 = 1, n_chunks = 1;
     int64_t bits_per_row = 0, tilesA = 0, tilesB = 0;
     unsigned long long cand_cap_used = 0, items_cap_used = 0;
-    bool ran_two_level = false;
+    bool ran_two_level = false, ran_two_kernel = false;
+    unsigned long long queue_cap_used = 0;
     float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
 
     // CSR on the device: two owned slots (async uploads fill the idle one while a pass runs on the
@@ -120,12 +122,12 @@ struct bf_ctx {
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
     DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
-    DevBuf bitsA, bitsB, jlo, wprefix, nwork, items, cand, edges, parent, labels, counters, scratch, scratch2;
+    DevBuf bitsA, bitsB, foldsA[2], foldsB[2], jlo, jend, wprefix, nwork, items, queue, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
     // per-run event ring so that bf_sync can report sums over all runs since the last sync
     static constexpr int kRing = 128;
-    cudaEvent_t ring[kRing][4] = {};  // pass start, pairs start, pairs end, pass end
+    cudaEvent_t ring[kRing][5] = {};  // pass start, pairs start, pairs end, pass end, level-1 end
     int64_t runs_since_sync = 0;
     int64_t launches_since_sync = 0;
 };
@@ -170,7 +172,7 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
     return BF_OK;
 }
 
-int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
+int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBuf folds[2]) {
     if (n == 0) return BF_OK;
     const int64_t tiles = ceil_div(n, TILE);
     const size_t bytes = (size_t)tiles * c->n_chunks * c->K4 * TILE * 16;
@@ -178,10 +180,12 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits) {
     if (c->engine == BF_ENGINE_SKETCH) {
         int log2m = 0;
         while ((1 << log2m) < c->sketch_bits) ++log2m;
-        if (c->sketch_bits == 128) {
-            k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>());
-        } else if (c->sketch_bits == 256) {
-            k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>());
+        if (c->sketch_bits == 128 || c->sketch_bits == 256) {
+            for (int f = 0; f < 2; ++f) TRY(folds[f].ensure((size_t)tiles * TILE * sizeof(uint32_t)));
+            if (c->sketch_bits == 128)
+                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>());
+            else
+                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>());
         } else {
             const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
             k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
@@ -228,6 +232,40 @@ int dispatch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_
     if (c->K4 == 1) return two ? launch_pairs<1, BF_STAGES_SMALL, true>(c, A, B, nA, nB, tri) : launch_pairs<1, BF_STAGES_SMALL, false>(c, A, B, nA, nB, tri);
     if (c->K4 == 2) return two ? launch_pairs<2, BF_STAGES_SMALL, true>(c, A, B, nA, nB, tri) : launch_pairs<2, BF_STAGES_SMALL, false>(c, A, B, nA, nB, tri);
     return two ? launch_pairs<4, 4, true>(c, A, B, nA, nB, tri) : launch_pairs<4, 4, false>(c, A, B, nA, nB, tri);
+}
+
+// level 1 on the fold planes (persistent, one CTA per SM) + level 2 on the queue
+int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device & 63]) {
+        CK(cudaFuncSetAttribute(k_pairs_l1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_pairs_l1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_pairs_l1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM_BYTES));
+        attr_set[c->device & 63] = true;
+    }
+    const uint32_t* fa = (c->has_query ? c->foldsA[0] : c->foldsB[0]).as<uint32_t>();
+    const uint32_t* fb = c->foldsB[1].as<uint32_t>();
+    auto l1 = k_pairs_l1<0>;
+    if (c->max_dist == 1) l1 = k_pairs_l1<1>;
+    else if (c->max_dist == 2) l1 = k_pairs_l1<2>;
+    int bps = c->blocks_per_sm;
+    if (bps <= 0) {  // two CTAs per SM when the register file allows it: more warps to hide POPC/min latency
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, l1, PAIR_THREADS, L1_SMEM_BYTES));
+        bps = std::max(1, std::min(bps, 2));
+    }
+    l1<<<(unsigned)(c->num_sms * bps), PAIR_THREADS, L1_SMEM_BYTES, c->stream>>>(
+        fa, fb, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, c->rank,
+        c->world, 1u, c->queue.as<int2>(), c->queue_cap_used, c->counters.as<DevCounters>());
+    CKLC(c);
+    CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
+    if (c->K4 == 1)
+        k_pairs_l2<1><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+                                                            tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
+    else
+        k_pairs_l2<2><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+                                                            tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
+    CKLC(c);
+    return BF_OK;
 }
 
 int finish_labels(bf_ctx* c) {
@@ -296,7 +334,7 @@ int bf_ctx_create(int device, void* stream, bf_ctx** ctx_out) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_upload_done);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_slot_free[i], cudaEventDisableTiming);
     for (int i = 0; i < bf_ctx::kRing && e == cudaSuccess; ++i)
-        for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&c->ring[i][j]);
+        for (int j = 0; j < 5 && e == cudaSuccess; ++j) e = cudaEventCreate(&c->ring[i][j]);
     if (e == cudaSuccess) {
         int rc = c->counters.ensure(sizeof(DevCounters));
         if (rc == BF_OK) rc = c->nwork.ensure(sizeof(unsigned long long));
@@ -320,7 +358,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->jlo, &c->wprefix, &c->nwork, &c->items, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->jlo, &c->jend, &c->queue, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -354,6 +392,9 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "items_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "items_capacity must be >= 0");
         c->items_capacity = value;
+    } else if (k == "units_capacity") {
+        if (value < 0) return fail(BF_ERR_INVALID, "units_capacity must be >= 0");
+        c->units_capacity = value;
     } else if (k == "blocks_per_sm") {
         if (value < 0 || value > 8) return fail(BF_ERR_INVALID, "blocks_per_sm must be in [0, 8]");
         c->blocks_per_sm = (int)value;
@@ -512,7 +553,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     }
     c->tilesA = ceil_div(nA, TILE);
     c->tilesB = ceil_div(nB, TILE);
-    c->ran_two_level = c->engine == BF_ENGINE_SKETCH && c->n_chunks == 1 && c->two_level;
+    c->ran_two_kernel = c->engine == BF_ENGINE_SKETCH && c->two_level && (c->sketch_bits == 128 || c->sketch_bits == 256);
+    c->ran_two_level = !c->ran_two_kernel && c->engine == BF_ENGINE_SKETCH && c->n_chunks == 1 && c->two_level;
 
     cudaEvent_t* ring = c->ring[c->runs_since_sync % bf_ctx::kRing];
     CK(cudaEventRecord(c->ev[0], c->stream));
@@ -537,17 +579,20 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(c->ev[1], c->stream));
     if (active) {
         // ---- K1: bit-pack
-        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB));
-        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA));
+        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB));
+        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA));
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
     if (active) {
         // ---- K2b: schedule
         TRY(c->jlo.ensure((size_t)c->tilesA * sizeof(int32_t)));
         TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
+        TRY(c->jend.ensure((size_t)c->tilesA * sizeof(int32_t)));
+        const int group = c->ran_two_kernel ? L1_GROUP : 1;
         k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
-            keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1,
-            c->jlo.as<int32_t>(), c->wprefix.as<unsigned long long>());
+            keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1, group,
+            c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),
+            &c->counters.as<DevCounters>()->n_tilepairs);
         CKLC(c);
         CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
         k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
@@ -570,7 +615,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             c->items_cap_used = icap;
             k_expand_items<<<c->num_sms * 8, 256, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(),
                                                                   c->tilesA, c->nwork.as<unsigned long long>(), icap,
-                                                                  c->items.as<int2>());
+                                                                  c->items.as<int2>(), group, c->jend.as<int32_t>());
             CKLC(c);
         }
         // candidate buffer
@@ -579,6 +624,11 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         TRY(c->cand.ensure((size_t)cap * sizeof(uint2)));
         c->cand_cap_used = cap;
         if (c->want_edges) TRY(c->edges.ensure((size_t)cap * sizeof(uint2)));
+        if (c->ran_two_kernel) {
+            unsigned long long qcap = c->units_capacity > 0 ? (unsigned long long)c->units_capacity : (1ull << 23);
+            TRY(c->queue.ensure((size_t)qcap * sizeof(int2)));
+            c->queue_cap_used = qcap;
+        }
     }
     CK(cudaEventRecord(c->ev[3], c->stream));
     CK(cudaEventRecord(ring[1], c->stream));
@@ -587,8 +637,13 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         const uint4* A = (c->has_query ? c->bitsA : c->bitsB).as<uint4>();
         const uint4* B = c->bitsB.as<uint4>();
         const int tri = c->has_query ? 0 : 1;
-        TRY(dispatch_pairs(c, A, B, nA, nB, tri));
+        if (c->ran_two_kernel) {
+            TRY(launch_two_kernel(c, A, B, nA, nB, tri));
+        } else {
+            TRY(dispatch_pairs(c, A, B, nA, nB, tri));
+        }
     }
+    if (!(active && c->ran_two_kernel)) CK(cudaEventRecord(ring[4], c->stream));  // no separate level-1 kernel ran
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaEventRecord(ring[2], c->stream));
     if (active) {
@@ -710,17 +765,26 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
             st->pairs_band = (int64_t)h.band_ab - Q - ((int64_t)h.band_aa - Q) / 2;
             st->tiles_total = c->tilesA * c->tilesB;
         }
-        st->tiles_band = (int64_t)nwork;
-        st->tiles_rank = (int64_t)nwork > c->rank ? ((int64_t)nwork - c->rank + c->world - 1) / c->world : 0;
+        st->tiles_band = (int64_t)h.n_tilepairs;
+        if (c->ran_two_kernel) st->tiles_rank = (int64_t)h.tilepairs_rank;
+        else st->tiles_rank = (int64_t)nwork > c->rank ? ((int64_t)nwork - c->rank + c->world - 1) / c->world : 0;
         st->pairs_evaluated = st->tiles_rank * TILE * TILE;
         st->n_candidates = (int64_t)h.n_cand;
         st->n_edges = (int64_t)h.n_edges;
         st->n_components = h.n_comp;
-        st->l2_warp_items = (int64_t)h.l2_warp_items;
         {
             const int64_t words = c->bits_per_row / 32;
-            st->popc32_executed = c->ran_two_level ? st->pairs_evaluated + (int64_t)h.l2_warp_items * 1024 * words
-                                                   : st->pairs_evaluated * words;
+            if (c->ran_two_kernel) {
+                // level 1: one 32-bit test per pair, half of them by POPC when max_dist is 1 or 2 (the other
+                // half runs POPC-free on the ALU/FMA pipes); level 2: `words` POPC per pair of every queued 32-pair unit
+                st->l2_warp_items = (int64_t)std::min<unsigned long long>(h.n_units, c->queue_cap_used);
+                const int64_t l1 = (c->max_dist == 1 || c->max_dist == 2) ? st->pairs_evaluated / 2 : st->pairs_evaluated;
+                st->popc32_executed = l1 + st->l2_warp_items * 32 * words;
+            } else {
+                st->l2_warp_items = (int64_t)h.l2_warp_items;
+                st->popc32_executed = c->ran_two_level ? st->pairs_evaluated + st->l2_warp_items * 1024 * words
+                                                       : st->pairs_evaluated * words;
+            }
         }
         float ms = 0;
         if (c->ms_h2d < 0) {
@@ -750,11 +814,27 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
         for (int64_t k = 0; k < covered; ++k) {
             cudaEvent_t* r = c->ring[(c->runs_since_sync - 1 - k) % bf_ctx::kRing];
             CK(cudaEventElapsedTime(&ms, r[1], r[2])); st->ms_pairs_sum += ms;
+            if (c->ran_two_kernel) { CK(cudaEventElapsedTime(&ms, r[1], r[4])); st->ms_l1_sum += ms; }
             CK(cudaEventElapsedTime(&ms, r[0], r[3])); st->ms_total_sum += ms;
         }
     }
     c->runs_since_sync = 0;
     c->launches_since_sync = 0;
+    if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
+        char buf[256];
+        if (h.n_units > c->queue_cap_used) {
+            c->units_capacity = (int64_t)(h.n_units + h.n_units / 4 + 1024);
+            snprintf(buf, sizeof buf, "level-2 queue overflow: %llu units > capacity %llu; units_capacity raised, run again",
+                     (unsigned long long)h.n_units, c->queue_cap_used);
+            return fail(BF_ERR_OVERFLOW, buf);
+        }
+        if (nwork > c->items_cap_used) {
+            c->items_capacity = (int64_t)(nwork + 1024);
+            snprintf(buf, sizeof buf, "work list overflow: %llu items > capacity %llu; items_capacity raised, run again",
+                     (unsigned long long)nwork, c->items_cap_used);
+            return fail(BF_ERR_OVERFLOW, buf);
+        }
+    }
     if (overflow) {
         char buf[256];
         snprintf(buf, sizeof buf, "candidate buffer overflow: %llu candidates > capacity %llu; set cand_capacity and run again",

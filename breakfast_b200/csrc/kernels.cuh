@@ -37,7 +37,10 @@ struct DevCounters {
     unsigned long long n_edges;     // verified edges
     unsigned long long band_ab;     // ordered in-band (a,b) count, A side vs B side (incl. self)
     unsigned long long band_aa;     // ordered in-band (a,a') count inside the A side (rectangle runs)
-    unsigned long long l2_warp_items;  // (warp, work item) pairs of the pair kernel that needed the full-width pass
+    unsigned long long l2_warp_items;  // (warp, tile pair) units that needed the full-width pass
+    unsigned long long n_tilepairs;    // band tile pairs of the whole job (when work items group several column tiles)
+    unsigned long long tilepairs_rank; // tile pairs this rank's level-1 kernel evaluated
+    unsigned long long n_units;        // level-2 queue cursor (may exceed capacity -> overflow)
     unsigned int n_comp;
     unsigned int pad;
 };
@@ -207,9 +210,12 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, i
 // K2b: band-pruned tile schedule.  keys are sorted ascending, so tile min/max are its ends and the
 // B tiles that can hold an in-band partner of A tile I form one contiguous range [jlo, jlo+count).
 // ------------------------------------------------------------------------------------------
+// `group` column tiles form one work item (1 for the single-kernel path, L1_GROUP for the two-kernel
+// path); count[I] = number of work items of row tile I, *n_tilepairs += number of tile pairs.
 __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const uint32_t* __restrict__ keysB,
-                           int64_t nB, int max_dist, int triangular, int32_t* __restrict__ jlo,
-                           unsigned long long* __restrict__ count) {
+                           int64_t nB, int max_dist, int triangular, int group, int32_t* __restrict__ jlo,
+                           int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
+                           unsigned long long* __restrict__ n_tilepairs) {
     const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
     int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (I >= tA) return;
@@ -235,7 +241,10 @@ __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const
     int64_t end = l;
     if (triangular && first < I) first = I;
     jlo[I] = (int32_t)first;
-    count[I] = end > first ? (unsigned long long)(end - first) : 0ull;
+    jend[I] = (int32_t)max(end, first);
+    const unsigned long long tp = end > first ? (unsigned long long)(end - first) : 0ull;
+    count[I] = (tp + group - 1) / group;
+    if (tp) atomicAdd(n_tilepairs, tp);
 }
 
 // ordered in-band count: for every x in X, #{y in Y : |key_x - key_y| <= d}
@@ -275,6 +284,11 @@ __host__ __device__ inline size_t word_offset(int64_t tile, int n_chunks, int K4
     const int chunk = wd / wpc, r = wd - chunk * wpc;
     return ((((size_t)tile * n_chunks + chunk) * K4 + (r >> 2)) * TILE + row) * 4 + (r & 3);
 }
+
+// positions inside a 128-row fold tile: row-operand order (row = ty + 16 i  ->  ty*8 + i) and
+// column-operand order (row = lane + 32 j  ->  lane*4 + j)
+__host__ __device__ inline int fold_pos_a(int row) { return (row & 15) * 8 + (row >> 4); }
+__host__ __device__ inline int fold_pos_b(int row) { return (row & 31) * 4 + (row >> 5); }
 
 __device__ __forceinline__ uint32_t fold_hash(uint32_t col, int log2m) {
     return (col * 2654435761u) >> (32 - log2m);  // multiplicative hash -> [0, m)
@@ -325,7 +339,8 @@ template <int WORDS>
 __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restrict__ indptr,
                                                          const int32_t* __restrict__ indices,
                                                          const int32_t* __restrict__ perm, int64_t n, int log2m,
-                                                         uint32_t* __restrict__ bits) {
+                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
+                                                         uint32_t* __restrict__ foldB) {
     constexpr int K4 = WORDS / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
@@ -357,6 +372,14 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
             const int row = warp + 8 * k;  // rows past n stay all-zero (never emitted: index check in k_pairs)
 #pragma unroll
             for (int g = 0; g < K4; ++g) dst[g * TILE + row] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+            // level-1 operand: the sketch folded once more to 32 bits, stored twice so that both the
+            // row-operand (8 rows of a warp contiguous) and the column-operand (4 rows of a lane
+            // contiguous) of k_pairs_l1 are single 128-bit shared loads
+            uint32_t f = 0;
+#pragma unroll
+            for (int t = 0; t < WORDS; ++t) f ^= w[t];
+            foldA[tile * TILE + fold_pos_a(row)] = f;
+            foldB[tile * TILE + fold_pos_b(row)] = f;
         }
     }
 }
@@ -420,9 +443,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // K2c: explicit work list.  items[w] = (I, J) for every band tile pair, so that the pair kernel's
 // producer needs one load per item instead of a binary search.
 // ------------------------------------------------------------------------------------------
+// With group > 1 an item covers column tiles J0 .. J0+cnt-1 (cnt <= group <= 4) and is stored as
+// (I, J0 | (cnt-1) << 29); jcount[I] (tile pairs of row tile I) is recomputed from the next prefix.
 __global__ void k_expand_items(const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo,
                                int64_t tilesA, const unsigned long long* __restrict__ n_work,
-                               unsigned long long cap, int2* __restrict__ items) {
+                               unsigned long long cap, int2* __restrict__ items, int group,
+                               const int32_t* __restrict__ jend) {
     const unsigned long long W = min(*n_work, cap);
     for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < W;
          w += (unsigned long long)gridDim.x * blockDim.x) {
@@ -431,7 +457,13 @@ __global__ void k_expand_items(const unsigned long long* __restrict__ wprefix, c
             const int64_t mid = (lo + hi + 1) >> 1;
             if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
         }
-        items[w] = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+        if (group == 1) {
+            items[w] = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+        } else {
+            const int j0 = __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])) * group;
+            const int cnt = min(group, __ldg(&jend[lo]) - j0);
+            items[w] = make_int2((int)lo, j0 | ((cnt - 1) << 29));
+        }
     }
 }
 
@@ -632,6 +664,175 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
         }
     }
     if (TWO_LEVEL && lane == 0 && l2_count) atomicAdd(&counters->l2_warp_items, (unsigned long long)l2_count);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (two-kernel form, single-chunk sketches): level 1 on the 32-bit fold planes, level 2 on a queue.
+//
+// k_pairs_l1: persistent, warp 16 = producer (one bulk copy of the row tile's folds + one of up to
+//   L1_GROUP consecutive column tiles' folds per work item), warps 0-15 = consumers.  Thread
+//   (warp, lane) tests the 8 x 4 pairs (warp+16i, lane+32j) of every column tile of the item with ONE
+//   32-bit XOR per pair and either POPC (columns j = 0,1) or, for max_dist 1 and 2, the POPC-free
+//   "clear the lowest set bit max_dist times, then compare with 0" on the ALU pipe (columns j = 2,3),
+//   so that the XU (POPC), ALU and FMA pipes share the work.  Only running minima are kept.  A thread
+//   whose 32 pairs of a tile pair hold a survivor appends the unit (I, J, warp, lane) to the queue.
+// k_pairs_l2: one thread per queued unit, operands straight from L2 (the sketches are L2-resident),
+//   full-width XOR/POPC on the unit's 32 pairs, threshold, candidate emission.  Perfectly balanced,
+//   no ring, no inter-warp coupling.
+// ------------------------------------------------------------------------------------------
+constexpr int L1_GROUP = 4;
+constexpr int L1_STAGES = 8;
+constexpr int L1_STAGE_BYTES = (1 + L1_GROUP) * TILE * 4;
+constexpr int L1_SMEM_BYTES = L1_STAGES * L1_STAGE_BYTES + L1_STAGES * (8 + 8 + 8);
+
+template <int T>  // T = max_dist if it is 1 or 2 (hybrid XU/ALU test), 0 = POPC only with a runtime threshold
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ foldB, const int2* __restrict__ items,
+           unsigned long long items_cap, const unsigned long long* __restrict__ n_work, int threshold, int rank,
+           int world, uint32_t one, int2* __restrict__ queue, unsigned long long queue_cap,
+           DevCounters* __restrict__ counters) {
+    // `one` is 1, passed as an argument so that y * one - 1 stays an IMAD: the decrement of the POPC-free
+    // test then runs on the FMA pipe and the ALU pipe (XOR, AND, min) stops being the bottleneck
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L1_STAGES * L1_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + L1_STAGES;
+    int2* meta = reinterpret_cast<int2*>(empty_bar + L1_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < L1_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned long long W = min(*n_work, items_cap);
+    const unsigned long long first = (unsigned long long)rank + (unsigned long long)world * blockIdx.x;
+    const unsigned long long stride = (unsigned long long)world * gridDim.x;
+
+    if (warp == PAIR_CONSUMER_WARPS) {
+        uint32_t it = 0;
+        unsigned long long tp = 0;
+        for (unsigned long long k0 = 0;; k0 += 32) {
+            if (first + k0 * stride >= W) break;
+            const unsigned long long w = first + (k0 + lane) * stride;
+            int2 mine = make_int2(0, 0);
+            if (w < W) mine = __ldg(&items[w]);
+            for (int l = 0; l < 32; ++l) {
+                if (first + (k0 + l) * stride >= W) break;
+                const int Il = __shfl_sync(0xffffffffu, mine.x, l), Jp = __shfl_sync(0xffffffffu, mine.y, l);
+                if (lane == 0) {
+                    const int J0 = Jp & 0x1fffffff, cnt = ((unsigned)Jp >> 29) + 1;
+                    const uint32_t stage = it % L1_STAGES, ph = (it / L1_STAGES) & 1u;
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    meta[stage] = make_int2(Il, Jp);
+                    unsigned char* sa = smem + stage * L1_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(1 + cnt) * TILE * 4);
+                    bulk_g2s(sa, foldA + (size_t)Il * TILE, TILE * 4, &full_bar[stage]);
+                    bulk_g2s(sa + TILE * 4, foldB + (size_t)J0 * TILE, (uint32_t)cnt * TILE * 4, &full_bar[stage]);
+                    ++it;
+                    tp += cnt;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0 && tp) atomicAdd(&counters->tilepairs_rank, tp);
+        return;
+    }
+
+    uint32_t it = 0;
+    for (unsigned long long w = first; w < W; w += stride, ++it) {
+        const uint32_t stage = it % L1_STAGES, ph = (it / L1_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], ph);
+        const uint4* sA = reinterpret_cast<const uint4*>(smem + stage * L1_STAGE_BYTES);
+        const uint4* sB = sA + TILE / 4;
+        const int2 ij = meta[stage];
+        const int cnt = ((unsigned)ij.y >> 29) + 1;
+        const uint4 a0 = sA[warp * 2], a1 = sA[warp * 2 + 1];  // folds of rows warp + 16 i, i = 0..7
+        const uint32_t fa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        for (int jt = 0; jt < cnt; ++jt) {
+            const uint4 b = sB[jt * (TILE / 4) + lane];        // folds of rows lane + 32 j, j = 0..3
+            bool mine;
+            if constexpr (T == 0) {
+                int mn = 64;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    mn = min(mn, min(__popc(fa[i] ^ b.x), __popc(fa[i] ^ b.y)));
+                    mn = min(mn, min(__popc(fa[i] ^ b.z), __popc(fa[i] ^ b.w)));
+                }
+                mine = mn <= threshold;
+            } else {
+                int mn = 64;
+                uint32_t mz = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    mn = min(mn, min(__popc(fa[i] ^ b.x), __popc(fa[i] ^ b.y)));
+                    uint32_t y2 = fa[i] ^ b.z, y3 = fa[i] ^ b.w;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {  // popc(y) <= T  <=>  y with its T lowest set bits cleared == 0
+                        y2 &= y2 * one - 1u;
+                        y3 &= y3 * one - 1u;
+                    }
+                    mz = min(mz, min(y2, y3));
+                }
+                mine = (mn <= T) || (mz == 0u);
+            }
+            if (mine) {  // rare: this thread's 32 pairs of tile pair (I, J0 + jt) go to level 2
+                const unsigned long long pos = atomicAdd(&counters->n_units, 1ull);
+                if (pos < queue_cap) queue[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+}
+
+template <int K4>
+__global__ void __launch_bounds__(256)
+k_pairs_l2(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int64_t nA, int64_t nB,
+           const int2* __restrict__ queue, unsigned long long queue_cap, int threshold, int triangular,
+           uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    // one THREAD per queued unit = the 8 x 4 pairs (ty + 16 i, lane + 32 j) of tile pair (I, J) that a
+    // level-1 thread could not reject; operands straight from L2
+    const unsigned long long n_units = min(counters->n_units, queue_cap);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u < n_units; u += stride) {
+        const int2 unit = __ldg(&queue[u]);
+        const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
+        const uint4* gA = bitsA + (size_t)I * (K4 * TILE);
+        const uint4* gB = bitsB + (size_t)J * (K4 * TILE);
+        int acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+#pragma unroll
+        for (int k4 = 0; k4 < K4; ++k4) {
+            uint4 b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = __ldg(&gB[k4 * TILE + tx + 32 * j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 a = __ldg(&gA[k4 * TILE + ty + 16 * i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[i][j] += __popc(a.x ^ b[j].x) + __popc(a.y ^ b[j].y) + __popc(a.z ^ b[j].z) + __popc(a.w ^ b[j].w);
+            }
+        }
+        const int64_t gi0 = (int64_t)I * TILE + ty, gj0 = (int64_t)J * TILE + tx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (acc[i][j] <= threshold) {
+                    const int64_t gi = gi0 + 16 * i, gj = gj0 + 32 * j;
+                    if (gi < nA && gj < nB && (!triangular || gi < gj)) {
+                        unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
+                        if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
+                    }
+                }
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,7 +26,8 @@ class Stats(C.Structure):
         (n, C.c_double) for n in ("ms_h2d", "ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge",
                                   "ms_d2h", "ms_total")] + [
         ("runs_since_sync", C.c_int64), ("kernel_launches", C.c_int64), ("ms_pairs_sum", C.c_double),
-        ("ms_total_sum", C.c_double), ("l2_warp_items", C.c_int64), ("popc32_executed", C.c_int64)]
+        ("ms_total_sum", C.c_double), ("l2_warp_items", C.c_int64), ("popc32_executed", C.c_int64),
+        ("ms_l1_sum", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
