@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
         }
     }
     uint4* dst = reinterpret_cast<uint4*>(bits) + (size_t)tile * (K4 * TILE);
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < TILE / 8; ++k) {
         const int64_t b = __shfl_sync(0xffffffffu, my_b, k), e = __shfl_sync(0xffffffffu, my_e, k);
         uint32_t w[WORDS];
@@ -967,10 +967,12 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                     // distance is larger the count can only be too small, i.e. the pair is still rejected.
                     // No data-dependent addressing: all loads of a sweep are independent and coalesced.
                     if constexpr (DWIN > 0) {
-                        // compile-time window: every load of a sweep is independent and the sweeps are
-                        // unrolled, so a candidate costs about one memory round trip
-#pragma unroll 4
-                        for (int64_t k = lane; k < la; k += 32) {
+                        // compile-time window and four predicated sweeps (rows up to 128 columns): every load
+                        // of a candidate is independent of the others and issued back to back, so a candidate
+                        // costs about one memory round trip; longer rows continue in the loop below.
+                        // (Four candidates per warp in 8-lane groups was tried: slower, the kernel is bound by
+                        // the scattered 360-byte row reads, ~545 MB per pass, not by latency.)
+                        auto match_at = [&](int64_t k) {
                             const int x = __ldg(&indices[ia + k]);
                             bool hit = false;
 #pragma unroll
@@ -978,8 +980,14 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                                 const int64_t j = k + o;
                                 if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
                             }
-                            inter += hit ? 1 : 0;
+                            return hit ? 1 : 0;
+                        };
+#pragma unroll
+                        for (int sweep = 0; sweep < 4; ++sweep) {
+                            const int64_t k = lane + 32 * sweep;
+                            if (k < la) inter += match_at(k);
                         }
+                        for (int64_t k = lane + 128; k < la; k += 32) inter += match_at(k);
                     } else {
                         for (int64_t k = lane; k < la; k += 32) {
                             const int x = __ldg(&indices[ia + k]);
