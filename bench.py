@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
     ap.add_argument("--engine", default="sketch", choices=["sketch", "full"])
     ap.add_argument("--two-level", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--level1", type=int, default=1, choices=[0, 1], help="1 = int8 mma.sync level 1 (default), 0 = integer pipes")
     ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -220,14 +221,14 @@ def main():
     p_labels = C.c_void_p()
     assert lib.bf_pinned_alloc(labels_host.nbytes, C.byref(p_labels)) == 0
 
-    peaks = {name: _native.measure_peak(name, local_rank) for name in ("popc32", "lop3")}  # also warms the clocks
+    peaks = {name: _native.measure_peak(name, local_rank) for name in ("popc32", "lop3", "imma_s8")}  # also warms the clocks
 
     # a real (non-default) torch stream: the library enqueues on it, torch events and NCCL order against it
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits,
-                          two_level=args.two_level)
+                          two_level=args.two_level, level1=args.level1)
     ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
     runner = RankRunner(ctx, n, rank, world)
 
@@ -261,7 +262,18 @@ def main():
     runs = max(1, min(st.runs_since_sync, 128))
     ms_pairs = st.ms_pairs_sum / runs
     two_kernel = args.engine == "sketch" and args.two_level and st.bits_per_row in (128, 256)
-    if two_kernel:
+    if two_kernel and args.level1 == 1:
+        # dominant kernel = k_pairs_l1_imma: one m16n8k32 int8 MMA per 128 pairs = 32 int8 MACs per evaluated pair
+        # (DESIGN.md section 3); bound = the tensor pipe as reachable through mma.sync, peak measured in this process
+        ms_kernel = st.ms_l1_sum / runs
+        kernel_name = f"k_pairs_l1_imma (int8 mma.sync on the +-1 expanded 32-bit folds of {st.bits_per_row}-bit sketches)"
+        bound, unit_r, peak = "tensor", "Gint8-MAC/s (mma.sync m16n8k32)", peaks["imma_s8"]
+        ops_per_launch = int(st.pairs_evaluated * 32)
+        achieved = ops_per_launch / (ms_kernel * 1e-3) / 1e9
+        extra = {"macs_per_pair": 32, "level2_units": st.l2_warp_items, "ms_level2": (st.ms_pairs_sum - st.ms_l1_sum) / runs,
+                 "note": "tcgen05 peak is 4x the mma.sync rate, but with K = 32 its TMEM accumulator round trip is exposed "
+                         "(tools/experiments/l1_tcgen05_kernel.cuh.txt); the register-accumulator path is the faster one here"}
+    elif two_kernel:
         # dominant kernel = k_pairs_l1<T>.  Per evaluated pair it executes:
         #   T = max_dist in {1,2}: 1 XOR + T/2 AND + 1/2 min on the ALU pipe, 1/2 POPC on the XU pipe, T/2 IMAD (FMA)
         #   otherwise            : 1 XOR + 1/2 min on the ALU pipe, 1 POPC on the XU pipe
@@ -291,7 +303,8 @@ def main():
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            key = ("k_pairs_l1" if two_kernel else "k_pairs") + f"_{args.engine}_{st.bits_per_row}_n{n}_w{world}"
+            key = (("k_pairs_l1_imma" if args.level1 == 1 else "k_pairs_l1") if two_kernel else "k_pairs") + \
+                f"_{args.engine}_{st.bits_per_row}_n{n}_w{world}"
             traffic = json.loads(tf.read_text()).get(key)
         except Exception:
             traffic = None
@@ -364,7 +377,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD if n == N_PROFILES else f"{n} profiles (override)", "max_dist": MAX_DIST,
-                       "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level),
+                       "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level), "level1": "imma" if args.level1 == 1 else "int_pipes",
                        "l2_warp_items": st.l2_warp_items, "pairs_evaluated": st.pairs_evaluated, "n_cols": n_cols, "nnz": int(indices.size),
                        "candidate_pairs": st.pairs_band, "pairs_total": st.pairs_total, "tiles_band": st.tiles_band,
                        "edges": None if world > 1 else st.n_edges, "components": st.n_components,
@@ -380,8 +393,8 @@ def main():
             "roofline": dict({"kernel": kernel_name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit_r,
                               "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms_kernel,
                               "ops_per_launch": ops_per_launch,
-                              "peak_source": "bf_measure_peak('lop3'/'popc32') measured in this process; MEASURED_PEAKS.json "
-                                             "holds only HBM and bf16 peaks and this kernel is bound by the integer pipes",
+                              "peak_source": "bf_measure_peak('imma_s8'/'lop3'/'popc32') measured in this process; MEASURED_PEAKS.json "
+                                             "holds only HBM and bf16 (cuBLAS/tcgen05) peaks, not the int8 mma.sync or integer-pipe rates that bind here",
                               "kernel_share_of_step": ms_kernel / (st.ms_total_sum / runs) if st.ms_total_sum else None}, **extra),
             "cpu_baseline": cpu,
             "phases_ms": {k: getattr(st, k) for k in ("ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge")},

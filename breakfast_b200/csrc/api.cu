@@ -93,6 +93,7 @@ struct bf_ctx {
     int64_t cand_capacity = 0;  // 0 = auto
     int blocks_per_sm = 0;      // 0 = occupancy
     int two_level = 1;
+    int level1 = 1;             // 1 = tensor cores (k_pairs_l1_imma, default), 0 = integer pipes (k_pairs_l1)
     int64_t items_capacity = 0;  // 0 = auto
     int64_t units_capacity = 0;  // 0 = auto (level-2 queue)
 
@@ -122,7 +123,7 @@ struct bf_ctx {
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
     DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
-    DevBuf bitsA, bitsB, foldsA[2], foldsB[2], jlo, jend, wprefix, nwork, items, queue, cand, edges, parent, labels, counters, scratch, scratch2;
+    DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
     // per-run event ring so that bf_sync can report sums over all runs since the last sync
@@ -172,7 +173,7 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
     return BF_OK;
 }
 
-int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBuf folds[2]) {
+int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBuf folds[2], DevBuf fold8[2]) {
     if (n == 0) return BF_OK;
     const int64_t tiles = ceil_div(n, TILE);
     const size_t bytes = (size_t)tiles * c->n_chunks * c->K4 * TILE * 16;
@@ -182,10 +183,17 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
         while ((1 << log2m) < c->sketch_bits) ++log2m;
         if (c->sketch_bits == 128 || c->sketch_bits == 256) {
             for (int f = 0; f < 2; ++f) TRY(folds[f].ensure((size_t)tiles * TILE * sizeof(uint32_t)));
+            uint32_t* f8a = nullptr;   // expanded row operand (fragment order) and column operand (row-major)
+            uint4* f8b = nullptr;
+            if (c->level1 == 1) {
+                for (int f = 0; f < 2; ++f) TRY(fold8[f].ensure((size_t)(tiles + L1_GROUP) * TILE * 32));  // + slack: a bulk copy never crosses the end
+                f8a = fold8[0].as<uint32_t>();
+                f8b = fold8[1].as<uint4>();
+            }
             if (c->sketch_bits == 128)
-                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>());
+                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>(), f8a, f8b);
             else
-                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>());
+                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>(), f8a, f8b);
         } else {
             const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
             k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
@@ -234,8 +242,33 @@ int dispatch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_
     return two ? launch_pairs<4, 4, true>(c, A, B, nA, nB, tri) : launch_pairs<4, 4, false>(c, A, B, nA, nB, tri);
 }
 
+// level 1 on the tensor cores (mma.sync int8 on the +-1 expanded folds) + level 2 on the queue
+int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device & 63]) {
+        CK(cudaFuncSetAttribute(k_pairs_l1_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, IMMA_SMEM_BYTES));
+        attr_set[c->device & 63] = true;
+    }
+    const uint32_t* f8a = (c->has_query ? c->fold8A[0] : c->fold8B[0]).as<uint32_t>();
+    const uint4* f8b = c->fold8B[1].as<uint4>();
+    k_pairs_l1_imma<<<(unsigned)c->num_sms, PAIR_THREADS, IMMA_SMEM_BYTES, c->stream>>>(
+        f8a, f8b, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, c->rank,
+        c->world, c->queue.as<int2>(), c->queue_cap_used, c->counters.as<DevCounters>());
+    CKLC(c);
+    CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
+    if (c->K4 == 1)
+        k_pairs_l2<1, true><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+                                                                  tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
+    else
+        k_pairs_l2<2, true><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+                                                                  tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
+    CKLC(c);
+    return BF_OK;
+}
+
 // level 1 on the fold planes (persistent, one CTA per SM) + level 2 on the queue
 int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
+    if (c->level1 == 1) return launch_two_kernel_imma(c, A, B, nA, nB, tri);
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
         CK(cudaFuncSetAttribute(k_pairs_l1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM_BYTES));
@@ -259,10 +292,10 @@ int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int
     CKLC(c);
     CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
     if (c->K4 == 1)
-        k_pairs_l2<1><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+        k_pairs_l2<1, false><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
                                                             tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     else
-        k_pairs_l2<2><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+        k_pairs_l2<2, false><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
                                                             tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
@@ -358,7 +391,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->jlo, &c->jend, &c->queue, &c->wprefix, &c->nwork, &c->items, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -392,6 +425,9 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "items_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "items_capacity must be >= 0");
         c->items_capacity = value;
+    } else if (k == "level1") {
+        if (value != 0 && value != 1) return fail(BF_ERR_INVALID, "level1 must be 0 (integer pipes) or 1 (tensor cores)");
+        c->level1 = (int)value;
     } else if (k == "units_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "units_capacity must be >= 0");
         c->units_capacity = value;
@@ -579,8 +615,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(c->ev[1], c->stream));
     if (active) {
         // ---- K1: bit-pack
-        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB));
-        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA));
+        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB, c->fold8B));
+        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA, c->fold8A));
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
     if (active) {
@@ -778,8 +814,12 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
                 // level 1: one 32-bit test per pair, half of them by POPC when max_dist is 1 or 2 (the other
                 // half runs POPC-free on the ALU/FMA pipes); level 2: `words` POPC per pair of every queued 32-pair unit
                 st->l2_warp_items = (int64_t)std::min<unsigned long long>(h.n_units, c->queue_cap_used);
-                const int64_t l1 = (c->max_dist == 1 || c->max_dist == 2) ? st->pairs_evaluated / 2 : st->pairs_evaluated;
-                st->popc32_executed = l1 + st->l2_warp_items * 32 * words;
+                if (c->level1 == 1) {  // tensor-core level 1: no POPC there
+                    st->popc32_executed = st->l2_warp_items * 32 * words;
+                } else {
+                    const int64_t l1 = (c->max_dist == 1 || c->max_dist == 2) ? st->pairs_evaluated / 2 : st->pairs_evaluated;
+                    st->popc32_executed = l1 + st->l2_warp_items * 32 * words;
+                }
             } else {
                 st->l2_warp_items = (int64_t)h.l2_warp_items;
                 st->popc32_executed = c->ran_two_level ? st->pairs_evaluated + st->l2_warp_items * 1024 * words

@@ -290,6 +290,17 @@ __host__ __device__ inline size_t word_offset(int64_t tile, int n_chunks, int K4
 __host__ __device__ inline int fold_pos_a(int row) { return (row & 15) * 8 + (row >> 4); }
 __host__ __device__ inline int fold_pos_b(int row) { return (row & 31) * 4 + (row >> 5); }
 
+// 16 bits -> 16 int8 values (+1 for a clear bit, -1 for a set bit)
+__device__ __forceinline__ uint4 expand_pm1(uint32_t bits16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t spread = (((bits16 >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;  // bit i -> byte i
+        w[q] = 0x01010101u ^ (spread * 0xfeu);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ uint32_t fold_hash(uint32_t col, int log2m) {
     return (col * 2654435761u) >> (32 - log2m);  // multiplicative hash -> [0, m)
 }
@@ -340,7 +351,8 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
                                                          const int32_t* __restrict__ indices,
                                                          const int32_t* __restrict__ perm, int64_t n, int log2m,
                                                          uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
-                                                         uint32_t* __restrict__ foldB) {
+                                                         uint32_t* __restrict__ foldB, uint32_t* __restrict__ fold8a,
+                                                         uint4* __restrict__ fold8b) {
     constexpr int K4 = WORDS / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
@@ -380,6 +392,26 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
             for (int t = 0; t < WORDS; ++t) f ^= w[t];
             foldA[tile * TILE + fold_pos_a(row)] = f;
             foldB[tile * TILE + fold_pos_b(row)] = f;
+            if (fold8b) {
+                // tensor-core operands: bit k of the fold -> int8 (+1 if clear, -1 if set), so that the int8 dot
+                // product of two rows is 32 - 2 popc(fa xor fb).
+                //  column operand: plain row-major, 32 bytes per row (a lane's B fragment = 8 contiguous bytes)
+                //  row operand: m16n8k32 A-fragment order - the 16 bytes {row r: k lo, row r+8: k lo, row r: k hi,
+                //  row r+8: k hi} of lane (r%8)*4 + w of m-tile r/16 are contiguous, so a fragment is one LDS.128
+                const uint4 e0 = expand_pm1(f & 0xffffu), e1 = expand_pm1(f >> 16);
+                uint4* tb = fold8b + (size_t)tile * (TILE * 2);
+                tb[row * 2 + 0] = e0;
+                tb[row * 2 + 1] = e1;
+                uint32_t* ta = fold8a + (size_t)tile * (TILE * 8);
+                const int m = row >> 4, h = (row >> 3) & 1, fr = row & 7;
+                const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};   // bytes 4q .. 4q+3
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t* frag = ta + ((m * 8 + fr) * 4 + w) * 4;
+                    frag[h] = words[2 * w];           // k lo of this lane's slice (bytes 8w .. 8w+3)
+                    frag[2 + h] = words[2 * w + 1];   // k hi (bytes 8w+4 .. 8w+7)
+                }
+            }
         }
     }
 }
@@ -499,7 +531,7 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
         const unsigned long long* __restrict__ n_work, int threshold, int triangular, int rank, int world,
         uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
     using L = PairSmem<K4, STAGES>;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     int2* meta = reinterpret_cast<int2*>(empty_bar + STAGES);
@@ -693,7 +725,7 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
            DevCounters* __restrict__ counters) {
     // `one` is 1, passed as an argument so that y * one - 1 stays an IMAD: the decrement of the POPC-free
     // test then runs on the FMA pipe and the ALU pipe (XOR, AND, min) stops being the bottleneck
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L1_STAGES * L1_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + L1_STAGES;
     int2* meta = reinterpret_cast<int2*>(empty_bar + L1_STAGES);
@@ -787,13 +819,131 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
     }
 }
 
-template <int K4>
+// ------------------------------------------------------------------------------------------
+// K3a'': level 1 on the tensor cores through mma.sync (SASS IMMA.16832.S8, register accumulators).
+// The pack kernel expands the 32-bit folds to +-1 int8 rows (32 B per row), so an m16n8k32 MMA gives
+// acc = 32 - 2 popc(fa xor fb) for 128 pairs, and popc <= max_dist  <=>  acc >= 32 - 2 max_dist.
+//   warp 16 = producer (same ring as k_pairs_l1, operands 4 KB per 128-row tile).
+//   warps 0-15: warp w takes the 8 column rows 8w .. 8w+7 of every column tile against all 128 rows of the
+//   row tile: the 8 A fragments (16 rows each) are loaded once per item and stay in registers, per column
+//   tile one 64-bit shared load gives the B fragment, 8 IMMAs produce 32 accumulators per thread, a 3-input
+//   max tree decides.  LDS.64 addresses row*32 + 8 (lane%4): conflict-free per half-warp.  The K order
+//   inside a row is permuted identically for both operands (bytes 8w..8w+3 <-> MMA k = 4w.., bytes
+//   8w+4..8w+7 <-> k = 16+4w..), which a dot product does not see.
+// Measured IMMA rate on the box: 1949 MAC/clk/SM = 60.9 pairs/clk/SM (tools/experiments/imma_rate.cu)
+// against ~27 pairs/clk/SM of the integer-pipe level 1; a tcgen05/TMEM variant was bit-exact but slower
+// (accumulator round-trip latency with K = 32, see tools/experiments/l1_tcgen05_kernel.cuh.txt).
+// ------------------------------------------------------------------------------------------
+constexpr int IMMA_STAGES = 6;
+constexpr int IMMA_TILE_BYTES = TILE * 32;
+constexpr int IMMA_STAGE_BYTES = (1 + L1_GROUP) * IMMA_TILE_BYTES;
+constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
+
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(0));
+}
+
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ fold8B, const int2* __restrict__ items,
+                unsigned long long items_cap, const unsigned long long* __restrict__ n_work, int max_dist, int rank,
+                int world, int2* __restrict__ queue, unsigned long long queue_cap, DevCounters* __restrict__ counters) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + IMMA_STAGES * IMMA_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + IMMA_STAGES;
+    int2* meta = reinterpret_cast<int2*>(empty_bar + IMMA_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IMMA_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned long long W = min(*n_work, items_cap);
+    const unsigned long long first = (unsigned long long)rank + (unsigned long long)world * blockIdx.x;
+    const unsigned long long stride = (unsigned long long)world * gridDim.x;
+
+    if (warp == PAIR_CONSUMER_WARPS) {
+        uint32_t it = 0;
+        unsigned long long tp = 0;
+        for (unsigned long long k0 = 0;; k0 += 32) {
+            if (first + k0 * stride >= W) break;
+            const unsigned long long w = first + (k0 + lane) * stride;
+            int2 mine = make_int2(0, 0);
+            if (w < W) mine = __ldg(&items[w]);
+            for (int l = 0; l < 32; ++l) {
+                if (first + (k0 + l) * stride >= W) break;
+                const int Il = __shfl_sync(0xffffffffu, mine.x, l), Jp = __shfl_sync(0xffffffffu, mine.y, l);
+                if (lane == 0) {
+                    const int J0 = Jp & 0x1fffffff, cnt = ((unsigned)Jp >> 29) + 1;
+                    const uint32_t stage = it % IMMA_STAGES, ph = (it / IMMA_STAGES) & 1u;
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    meta[stage] = make_int2(Il, Jp);
+                    unsigned char* sa = smem + stage * IMMA_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(1 + cnt) * IMMA_TILE_BYTES);
+                    bulk_g2s(sa, fold8A + (size_t)Il * (TILE * 8), IMMA_TILE_BYTES, &full_bar[stage]);
+                    bulk_g2s(sa + IMMA_TILE_BYTES, fold8B + (size_t)J0 * (TILE * 2), (uint32_t)cnt * IMMA_TILE_BYTES, &full_bar[stage]);
+                    ++it;
+                    tp += cnt;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0 && tp) atomicAdd(&counters->tilepairs_rank, tp);
+        return;
+    }
+
+    const int thr = 32 - 2 * max_dist;
+    const int frow = lane >> 2, fk = (lane & 3) * 8;   // B fragment: row inside the warp's 8 rows, byte offset of this lane's k slice
+    uint32_t it = 0;
+    for (unsigned long long w = first; w < W; w += stride, ++it) {
+        const uint32_t stage = it % IMMA_STAGES, ph = (it / IMMA_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], ph);
+        const unsigned char* sA = smem + stage * IMMA_STAGE_BYTES;
+        const unsigned char* sB = sA + IMMA_TILE_BYTES;
+        const int2 ij = meta[stage];
+        const int cnt = ((unsigned)ij.y >> 29) + 1;
+        // A fragments of the 8 m-tiles, stored in fragment order by the pack kernel: one LDS.128 each
+        uint4 a[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a[m] = reinterpret_cast<const uint4*>(sA)[m * 32 + lane];
+        for (int jt = 0; jt < cnt; ++jt) {
+            const uint2 b = *reinterpret_cast<const uint2*>(sB + jt * IMMA_TILE_BYTES + (8 * warp + frow) * 32 + fk);
+            // all 8 MMAs are issued back to back into their own accumulators, then four independent max chains
+            int c[8][4];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) imma_16832(c[m], a[m], b.x, b.y);
+            int mq[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                mq[t] = max(max(c[2 * t][0], c[2 * t][1]), max(c[2 * t][2], c[2 * t][3]));
+                mq[t] = max(mq[t], max(c[2 * t + 1][0], c[2 * t + 1][1]));
+                mq[t] = max(mq[t], max(c[2 * t + 1][2], c[2 * t + 1][3]));
+            }
+            const int mx = max(max(mq[0], mq[1]), max(mq[2], mq[3]));
+            if (mx >= thr) {  // rare: this thread's 16 x 2 pairs of tile pair (I, J0 + jt) go to level 2
+                const unsigned long long pos = atomicAdd(&counters->n_units, 1ull);
+                if (pos < queue_cap) queue[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+}
+
+// UNIT_IMMA = false: unit = the 8 x 4 pairs (ty + 16 i, tx + 32 j) of a k_pairs_l1 thread
+// UNIT_IMMA = true : unit = the 16 x 2 pairs (16 (i/2) + tx/4 + 8 (i%2), 8 ty + 2 (tx%4) + j) of a k_pairs_l1_imma
+//                    thread (the accumulator fragment of 8 m16n8k32 MMAs), i < 16, j < 2
+template <int K4, bool UNIT_IMMA>
 __global__ void __launch_bounds__(256)
 k_pairs_l2(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int64_t nA, int64_t nB,
            const int2* __restrict__ queue, unsigned long long queue_cap, int threshold, int triangular,
            uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
-    // one THREAD per queued unit = the 8 x 4 pairs (ty + 16 i, lane + 32 j) of tile pair (I, J) that a
-    // level-1 thread could not reject; operands straight from L2
+    // one THREAD per queued unit = the 32 pairs of tile pair (I, J) that a level-1 thread could not reject;
+    // operands straight from L2
     const unsigned long long n_units = min(counters->n_units, queue_cap);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u < n_units; u += stride) {
@@ -801,31 +951,34 @@ k_pairs_l2(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int
         const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
         const uint4* gA = bitsA + (size_t)I * (K4 * TILE);
         const uint4* gB = bitsB + (size_t)J * (K4 * TILE);
-        int acc[8][4];
+        constexpr int NI = UNIT_IMMA ? 16 : 8, NJ = UNIT_IMMA ? 2 : 4;
+        auto row_of = [&](int i) { return UNIT_IMMA ? 16 * (i >> 1) + (tx >> 2) + 8 * (i & 1) : ty + 16 * i; };
+        auto col_of = [&](int j) { return UNIT_IMMA ? 8 * ty + 2 * (tx & 3) + j : tx + 32 * j; };
+        int acc[NI][NJ];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+            for (int j = 0; j < NJ; ++j) acc[i][j] = 0;
 #pragma unroll
         for (int k4 = 0; k4 < K4; ++k4) {
-            uint4 b[4];
+            uint4 b[NJ];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = __ldg(&gB[k4 * TILE + tx + 32 * j]);
+            for (int j = 0; j < NJ; ++j) b[j] = __ldg(&gB[k4 * TILE + col_of(j)]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 a = __ldg(&gA[k4 * TILE + ty + 16 * i]);
+            for (int i = 0; i < NI; ++i) {
+                const uint4 a = __ldg(&gA[k4 * TILE + row_of(i)]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < NJ; ++j)
                     acc[i][j] += __popc(a.x ^ b[j].x) + __popc(a.y ^ b[j].y) + __popc(a.z ^ b[j].z) + __popc(a.w ^ b[j].w);
             }
         }
-        const int64_t gi0 = (int64_t)I * TILE + ty, gj0 = (int64_t)J * TILE + tx;
+        const int64_t gi0 = (int64_t)I * TILE, gj0 = (int64_t)J * TILE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 if (acc[i][j] <= threshold) {
-                    const int64_t gi = gi0 + 16 * i, gj = gj0 + 32 * j;
+                    const int64_t gi = gi0 + row_of(i), gj = gj0 + col_of(j);
                     if (gi < nA && gj < nB && (!triangular || gi < gj)) {
                         unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
                         if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);

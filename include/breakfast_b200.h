@@ -100,8 +100,10 @@ void bf_ctx_destroy(bf_ctx* ctx);
 /* Options: "engine" (bf_engine), "sketch_bits" (power of two, 128..2048),
  * "want_edges" (0/1), "cand_capacity" (entries), "blocks_per_sm",
  * "two_level" (0/1, default 1: 32-bit first-level fold inside the pair kernel for
- * single-chunk sketches; exact either way), "items_capacity" (entries of the
- * expanded work list, 0 = automatic). */
+ * single-chunk sketches; exact either way), "level1" (0 = level 1 on the integer
+ * pipes, 1 = on the tensor cores: int8 mma.sync on +-1 expanded folds; 128/256-bit
+ * sketches), "items_capacity" / "units_capacity" (entries of the expanded work list and
+ * of the level-2 queue, 0 = automatic). */
 int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
 
 /* ---- async, device-resident API (used by bench.py and the multi-rank host) */
@@ -176,7 +178,8 @@ int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_
 int bf_pinned_alloc(int64_t bytes, void** ptr_out);
 void bf_pinned_free(void* ptr);
 /* Register-resident pipe microbenchmarks on `device`; result in 1e9 lane-ops/s.
- * name: "popc32", "lop3", "iadd3", "xor_popc_add". Roofline denominators. */
+ * name: "popc32", "lop3", "iadd3", "xor_popc_add", or "imma_s8" (mma.sync m16n8k32 int8, result in
+ * 1e9 int8 MACs/s). Roofline denominators. */
 int bf_measure_peak(int32_t device, const char* name, double* gops_out);
 
 #ifdef __cplusplus

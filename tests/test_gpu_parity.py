@@ -95,6 +95,18 @@ def test_cluster_and_edges_match_oracle(n, max_dist, engine):
     assert st.pairs_band == band and st.pairs_total == n * (n - 1) // 2
 
 
+@pytest.mark.parametrize("max_dist", [1, 2, 3, 5])
+@pytest.mark.parametrize("level1", [0, 1])
+def test_both_level1_kernels_are_exact(level1, max_dist):
+    """level 1 on the integer pipes (POPC / POPC-free hybrid) and on the tensor cores (int8 mma.sync)"""
+    indptr, indices, n_cols = synth.generate(6000, seed=91).csr()
+    want, ne = oracle.cluster(indptr, indices, max_dist)
+    with _native.Context(level1=level1, sketch_bits=128) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(max_dist)
+        assert np.array_equal(ctx.download_labels(), want) and st.n_edges == ne
+
+
 @pytest.mark.parametrize("bits", [128, 256, 512, 1024, 2048])
 def test_every_sketch_width_is_exact(bits):
     indptr, indices, n_cols = synth.generate(3000, seed=77).csr()
@@ -121,7 +133,8 @@ def test_two_level_filter_changes_nothing(bits, max_dist):
                 assert st.l2_warp_items > 0
                 # 128/256-bit sketches: separate level-1 kernel whose test is POPC for half of the pairs when
                 # max_dist is 1 or 2; 512 bits: level 1 inside the single kernel, one POPC per pair
-                l1 = st.pairs_evaluated // 2 if (bits <= 256 and max_dist in (1, 2)) else st.pairs_evaluated
+                # (default level 1 for 128/256 bits = int8 mma.sync: no POPC at all there)
+                l1 = 0 if bits <= 256 else st.pairs_evaluated
                 unit = 32 if bits <= 256 else 1024
                 assert st.popc32_executed == l1 + st.l2_warp_items * unit * (bits // 32)
             else:

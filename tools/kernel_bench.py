@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--bps", type=int, default=0)
     ap.add_argument("--two-level", type=int, default=1)
+    ap.add_argument("--level1", type=int, default=0)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -52,6 +53,7 @@ def main():
         if bits:
             ck(lib.bf_ctx_set_option(ctx, b"sketch_bits", C.c_int64(bits)))
         ck(lib.bf_ctx_set_option(ctx, b"two_level", C.c_int64(args.two_level)))
+        ck(lib.bf_ctx_set_option(ctx, b"level1", C.c_int64(args.level1)))
         if args.bps:
             ck(lib.bf_ctx_set_option(ctx, b"blocks_per_sm", C.c_int64(args.bps)))
         ck(lib.bf_upload_csr(ctx, p64(indptr), p32(indices), C.c_int64(args.n), C.c_int32(n_cols), None, C.c_int64(0)))
