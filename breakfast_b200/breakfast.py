@@ -126,6 +126,31 @@ _PATTERNS = {
 _KEEP, _DROP, _INVALID = 0, 1, 2
 
 
+def _token_classifier(feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length):
+    """token -> _KEEP / _DROP / _INVALID under the reference's rules (breakfast.py:135-184)."""
+    if feature_type not in _PATTERNS:
+        print(f"The feature type (--var-type) you chose is not supported: '{feature_type}'")
+        sys.exit(1)
+    sub_re, ins_re, del_re = (re.compile(p) for p in _PATTERNS[feature_type])
+    upper_cut = reference_length - trim_end
+
+    def classify(tok):
+        hit = sub_re.match(tok)
+        if hit:
+            if hit.lastindex:
+                pos = int(hit.group(1))
+                if pos <= trim_start or pos >= upper_cut:
+                    return _DROP
+            return _KEEP
+        if ins_re.match(tok):
+            return _DROP if skip_ins else _KEEP
+        if del_re.match(tok):
+            return _DROP if skip_del else _KEEP
+        return _INVALID
+
+    return classify
+
+
 def filter_features(
     features,
     feature_sep,
@@ -148,26 +173,8 @@ def filter_features(
         return features
 
     is_raw = feature_type == "raw"
-    if not is_raw:
-        if feature_type not in _PATTERNS:
-            print(f"The feature type (--var-type) you chose is not supported: '{feature_type}'")
-            sys.exit(1)
-        sub_re, ins_re, del_re = (re.compile(p) for p in _PATTERNS[feature_type])
-    upper_cut = reference_length - trim_end
-
-    def classify(tok):
-        hit = sub_re.match(tok)
-        if hit:
-            if hit.lastindex:
-                pos = int(hit.group(1))
-                if pos <= trim_start or pos >= upper_cut:
-                    return _DROP
-            return _KEEP
-        if ins_re.match(tok):
-            return _DROP if skip_ins else _KEEP
-        if del_re.match(tok):
-            return _DROP if skip_del else _KEEP
-        return _INVALID
+    classify = None if is_raw else _token_classifier(feature_type, skip_ins, skip_del, trim_start, trim_end,
+                                                     reference_length)
 
     verdicts: dict = {}
     out = []
@@ -231,13 +238,22 @@ def _assign_cluster_ids(meta, labels, min_cluster_size):
 
 
 def cluster_features(meta, feature_sep, max_dist, min_cluster_size, input_cache, output_cache):
-    feat_matrix = sparse_feature_matrix(meta["feature"], feature_sep)
-    meta["n_features"] = feat_matrix.sum(axis=1)
-    n = feat_matrix.shape[0]
-    # strictly binary rows for the device (repeated tokens thermometer-coded)
-    indptr, indices, n_cols = engine.thermometer_binarise(
-        feat_matrix.indptr.astype(np.int64), feat_matrix.indices.astype(np.int64), feat_matrix.shape[1]
-    )
+    pre = meta.attrs.get("bf_csr") if hasattr(meta, "attrs") else None
+    if pre is not None and pre["n"] == len(meta):
+        # the native host path (hostfast.prepare) already tokenised the unique profiles
+        if pre["n_vocab"] == 0:
+            raise ValueError("unable to infer matrix dimensions")   # what scipy says to the reference here
+        meta["n_features"] = np.diff(pre["token_indptr"])
+        n = len(meta)
+        indptr, indices, n_cols = pre["bin_indptr"], pre["bin_indices"], pre["n_cols"]
+    else:
+        feat_matrix = sparse_feature_matrix(meta["feature"], feature_sep)
+        meta["n_features"] = feat_matrix.sum(axis=1)
+        n = feat_matrix.shape[0]
+        # strictly binary rows for the device (repeated tokens thermometer-coded)
+        indptr, indices, n_cols = engine.thermometer_binarise(
+            feat_matrix.indptr.astype(np.int64), feat_matrix.indices.astype(np.int64), feat_matrix.shape[1]
+        )
 
     cached = None
     try:

@@ -71,6 +71,23 @@ def build_synth(force: bool = False) -> Path:
     return SYNTH_LIB
 
 
+HOST_SRC = CSRC / "host_parse.cpp"
+HOST_LIB = PKG_DIR / "libbfhost.so"
+
+
+def build_host(force: bool = False) -> Path:
+    """g++ build of the native host-side parser (tokenise / filter / dedup / CSR); no CUDA involved."""
+    if not force and HOST_LIB.exists() and HOST_LIB.stat().st_mtime >= HOST_SRC.stat().st_mtime:
+        return HOST_LIB
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-O2", "-fPIC", "-shared", "-std=c++17", str(HOST_SRC), "-o", str(HOST_LIB)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
+    build_host(force="--force" in sys.argv)
     build_synth(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

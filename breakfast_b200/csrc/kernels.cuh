@@ -840,7 +840,8 @@ constexpr int IMMA_STAGE_BYTES = (1 + L1_GROUP) * IMMA_TILE_BYTES;
 constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
 
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+    // not volatile: a pure function of its operands, so the scheduler may overlap it with the max trees
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                  : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(0));
 }
@@ -910,21 +911,35 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
         uint4 a[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) a[m] = reinterpret_cast<const uint4*>(sA)[m * 32 + lane];
-        for (int jt = 0; jt < cnt; ++jt) {
-            const uint2 b = *reinterpret_cast<const uint2*>(sB + jt * IMMA_TILE_BYTES + (8 * warp + frow) * 32 + fk);
-            // all 8 MMAs are issued back to back into their own accumulators, then four independent max chains
-            int c[8][4];
+        // The four column tiles of an item are unrolled (missing ones predicated off): all B fragments are
+        // loaded up front and the MMAs are issued in groups of four m-tiles, so that the max tree of one group
+        // overlaps the tensor-pipe time of the next (software pipeline across the half-groups).
+        uint2 b[L1_GROUP];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) imma_16832(c[m], a[m], b.x, b.y);
-            int mq[4];
+        for (int jt = 0; jt < L1_GROUP; ++jt)
+            b[jt] = *reinterpret_cast<const uint2*>(sB + (jt < cnt ? jt : 0) * IMMA_TILE_BYTES + (8 * warp + frow) * 32 + fk);
+        int mxj[L1_GROUP];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                mq[t] = max(max(c[2 * t][0], c[2 * t][1]), max(c[2 * t][2], c[2 * t][3]));
-                mq[t] = max(mq[t], max(c[2 * t + 1][0], c[2 * t + 1][1]));
-                mq[t] = max(mq[t], max(c[2 * t + 1][2], c[2 * t + 1][3]));
+        for (int jt = 0; jt < L1_GROUP; ++jt) {
+            int mh[2];
+#pragma unroll
+            for (int hgrp = 0; hgrp < 2; ++hgrp) {
+                int c[4][4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) imma_16832(c[m], a[4 * hgrp + m], b[jt].x, b[jt].y);
+                int m0 = max(max(c[0][0], c[0][1]), max(c[0][2], c[0][3]));
+                int m1 = max(max(c[1][0], c[1][1]), max(c[1][2], c[1][3]));
+                m0 = max(m0, max(c[2][0], c[2][1]));
+                m1 = max(m1, max(c[2][2], c[2][3]));
+                m0 = max(m0, max(c[3][0], c[3][1]));
+                m1 = max(m1, max(c[3][2], c[3][3]));
+                mh[hgrp] = max(m0, m1);
             }
-            const int mx = max(max(mq[0], mq[1]), max(mq[2], mq[3]));
-            if (mx >= thr) {  // rare: this thread's 16 x 2 pairs of tile pair (I, J0 + jt) go to level 2
+            mxj[jt] = max(mh[0], mh[1]);
+        }
+#pragma unroll
+        for (int jt = 0; jt < L1_GROUP; ++jt) {
+            if (jt < cnt && mxj[jt] >= thr) {  // rare: this thread's 16 x 2 pairs of tile pair (I, J0 + jt) go to level 2
                 const unsigned long long pos = atomicAdd(&counters->n_units, 1ull);
                 if (pos < queue_cap) queue[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
             }

@@ -1,0 +1,123 @@
+"""Native fast path for the host side of the pipeline: filter_features + collapse_duplicates +
+sparse_feature_matrix (+ the binary CSR for the device) in one pass over the profiles.
+
+Semantics are those of the Python functions in breakfast.py (which stay the reference-shaped API and are
+what the tests of the reference call): the per-occurrence work (split, intern, filter, dedup, CSR) runs
+in csrc/host_parse.cpp, the classification of the DISTINCT tokens runs here with the same regular
+expressions as filter_features.  tests/test_host_cpu.py checks both paths against each other.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import build as _build
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(str(_build.build_host()))
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        lib.bfh_tokenise.restype = vp
+        lib.bfh_tokenise.argtypes = [C.c_char_p, i64, C.c_char, C.c_char_p, i32, i64]
+        for name in ("bfh_n_tokens", "bfh_distinct_bytes", "bfh_n_unique", "bfh_n_invalid", "bfh_token_nnz",
+                     "bfh_binary_nnz", "bfh_string_bytes"):
+            getattr(lib, name).restype = i64
+            getattr(lib, name).argtypes = [vp]
+        for name in ("bfh_n_distinct", "bfh_n_vocab", "bfh_n_cols"):
+            getattr(lib, name).restype = i32
+            getattr(lib, name).argtypes = [vp]
+        lib.bfh_get_distinct.argtypes = [vp, vp, vp]
+        lib.bfh_build.argtypes = [vp, vp, C.c_int]
+        lib.bfh_get_results.argtypes = [vp] + [vp] * 9
+        lib.bfh_free.argtypes = [vp]
+        _lib = lib
+    return _lib
+
+
+def available() -> bool:
+    try:
+        _load()
+        return True
+    except Exception:
+        return False
+
+
+def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length):
+    """meta (DataFrame[id, feature], raw profiles) -> meta_nodups exactly as
+    collapse_duplicates(meta with feature = filter_features(...)) would build it, with the token CSR and the
+    binary CSR of the unique profiles attached in `.attrs["bf_csr"]`.  Returns None when the input cannot
+    take the fast path (a profile containing NUL); the caller then uses the Python functions."""
+    from .breakfast import _INVALID, _token_classifier
+
+    feats = meta["feature"].tolist()
+    n_seq = len(feats)
+    if n_seq == 0 or any(isinstance(f, float) for f in feats):
+        return None
+    joined = "\x00".join(feats)
+    if joined.count("\x00") != n_seq - 1:
+        return None
+    lib = _load()
+    buf = joined.encode("utf-8")
+    sep_b = feature_sep.encode("utf-8")
+    if not sep_b:
+        return None
+    state = lib.bfh_tokenise(buf, len(buf), b"\x00", sep_b, len(sep_b), n_seq)
+    if not state:
+        return None
+    try:
+        nd = lib.bfh_n_distinct(state)
+        tok_bytes = C.create_string_buffer(max(1, lib.bfh_distinct_bytes(state)))
+        tok_off = np.empty(nd + 1, dtype=np.int64)
+        lib.bfh_get_distinct(state, tok_bytes, tok_off.ctypes.data)
+        raw = tok_bytes.raw
+        tokens = [raw[tok_off[i]:tok_off[i + 1]].decode("utf-8") for i in range(nd)]
+
+        filter_active = bool(skip_del or skip_ins or trim_start > 0 or trim_end > 0)
+        verdict = np.zeros(max(nd, 1), dtype=np.uint8)
+        if filter_active and feature_type != "raw":
+            classify = _token_classifier(feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length)
+            verdict[:nd] = [classify(t) for t in tokens]
+        lib.bfh_build(state, verdict.ctypes.data, int(filter_active))
+
+        n_unique = lib.bfh_n_unique(state)
+        codes = np.empty(n_seq, dtype=np.int32)
+        first_seq = np.empty(n_unique, dtype=np.int32)
+        invalid = np.empty(lib.bfh_n_invalid(state), dtype=np.int32)
+        u_ptr = np.empty(n_unique + 1, dtype=np.int64)
+        u_idx = np.empty(lib.bfh_token_nnz(state), dtype=np.int32)
+        b_ptr = np.empty(n_unique + 1, dtype=np.int64)
+        b_idx = np.empty(lib.bfh_binary_nnz(state), dtype=np.int32)
+        s_off = np.empty(n_unique + 1, dtype=np.int64)
+        s_bytes = C.create_string_buffer(max(1, lib.bfh_string_bytes(state)))
+        lib.bfh_get_results(state, codes.ctypes.data, first_seq.ctypes.data, invalid.ctypes.data, u_ptr.ctypes.data,
+                            u_idx.ctypes.data, b_ptr.ctypes.data, b_idx.ctypes.data, s_off.ctypes.data, s_bytes)
+        n_vocab, n_cols = lib.bfh_n_vocab(state), lib.bfh_n_cols(state)
+    finally:
+        lib.bfh_free(state)
+
+    if filter_active and feature_type != "raw":
+        assert _INVALID == 2
+        for t in invalid.tolist():
+            print(f"Skipping invalid feature: '{tokens[t]}'")
+    print(f"Number of duplicates: {n_seq - n_unique}")
+    order = np.argsort(codes, kind="stable")
+    bounds = np.concatenate(([0], np.cumsum(np.bincount(codes, minlength=n_unique))))
+    ids = meta["id"].to_numpy(dtype=object)[order]
+    grouped = np.empty(n_unique, dtype=object)
+    for g in range(n_unique):
+        grouped[g] = tuple(ids[bounds[g]:bounds[g + 1]])
+    sraw = s_bytes.raw
+    strings = [sraw[s_off[u]:s_off[u + 1]].decode("utf-8") for u in range(n_unique)]
+    nodups = pd.DataFrame({"id": pd.Series(grouped, dtype=object),
+                           "feature": pd.Series(strings, dtype=meta["feature"].dtype)})
+    print(f"Number of unique sequences: {n_unique}")
+    nodups.attrs["bf_csr"] = dict(n=n_unique, token_indptr=u_ptr, token_indices=u_idx, n_vocab=int(n_vocab),
+                                  bin_indptr=b_ptr, bin_indices=b_idx, n_cols=int(n_cols))
+    return nodups

@@ -209,6 +209,56 @@ def test_cli_max_dist_zero_goldens(case, tmp_path):
     helpers.assert_matches(case, case["expected"], helpers.run_cli(case["input"], case["opts"], tmp_path))
 
 
+# ------------------------------------------------------------------ native host path == Python host path
+def _python_path(meta, sep2, opts):
+    m = meta.copy()
+    m["feature"] = breakfast.filter_features(m["feature"], sep2, *opts)
+    nd = breakfast.collapse_duplicates(m)
+    indptr, indices, vocab = engine.tokenise(nd["feature"], sep2)
+    return nd, indptr, indices, len(vocab)
+
+
+@pytest.mark.parametrize("opts", [
+    ("covsonar_dna", True, True, 264, 228, 29903), ("covsonar_dna", False, False, 0, 0, 29903),
+    ("covsonar_dna", False, True, 3000, 3000, 29903), ("raw", True, True, 264, 228, 29903),
+    ("raw", False, False, 0, 0, 29903)], ids=lambda o: "-".join(map(str, o)))
+@pytest.mark.parametrize("table", ["synthetic/quirks.tsv", "synthetic/syn_dna.tsv.gz", "reference/testfile.tsv"])
+def test_native_host_path_equals_python_path(table, opts, capsys):
+    from breakfast_b200 import hostfast
+    assert hostfast.available()
+    meta = breakfast.read_input(GOLDEN / table, "\t", "accession", "dna_profile")
+    capsys.readouterr()
+    nd_py, indptr, indices, n_vocab = _python_path(meta, " ", opts)
+    out_py = capsys.readouterr().out
+    nd_c = hostfast.prepare(meta, " ", *opts)
+    out_c = capsys.readouterr().out
+    assert out_c == out_py                                        # same messages in the same order
+    assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
+    pre = nd_c.attrs["bf_csr"]
+    assert pre["n_vocab"] == n_vocab
+    assert np.array_equal(pre["token_indptr"], indptr) and np.array_equal(pre["token_indices"], indices)
+    bi, bx, nc = engine.thermometer_binarise(indptr, indices, n_vocab)
+    assert np.array_equal(pre["bin_indptr"], bi) and pre["n_cols"] == nc
+    # extra (repeat) columns may be numbered differently: compare the pairwise set distances instead
+    rows_c = [set(pre["bin_indices"][pre["bin_indptr"][i]:pre["bin_indptr"][i + 1]].tolist()) for i in range(min(len(nd_c), 60))]
+    rows_p = [set(bx[bi[i]:bi[i + 1]].tolist()) for i in range(min(len(nd_c), 60))]
+    for i in range(len(rows_c)):
+        assert sorted(rows_c[i]) == pre["bin_indices"][pre["bin_indptr"][i]:pre["bin_indptr"][i + 1]].tolist()
+        for j in range(len(rows_c)):
+            assert len(rows_c[i] ^ rows_c[j]) == len(rows_p[i] ^ rows_p[j])
+
+
+def test_native_host_path_nextclade_and_multichar_separator(capsys):
+    from breakfast_b200 import hostfast
+    meta = pd.DataFrame({"id": list("abcde"), "feature": ["C300T; G400A", "G400A; C300T; 12-15", "C300T; G400A; ; 5:ACG",
+                                                           "C300T; G400A", "é1; C300T"]})
+    opts = ("nextclade_dna", True, True, 10, 10, 29903)
+    nd_py, indptr, indices, n_vocab = _python_path(meta, "; ", opts)
+    nd_c = hostfast.prepare(meta, "; ", *opts)
+    assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
+    assert np.array_equal(nd_c.attrs["bf_csr"]["token_indices"], indices)
+
+
 # ------------------------------------------------------------------ no CPU fallback, no oracle in the product
 def test_product_never_imports_the_oracle():
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|ref_port|liboracle", re.M)

@@ -11,8 +11,10 @@ from tests import helpers
 from tests.helpers import GOLDEN, OracleEngine
 
 
-@pytest.fixture(autouse=True)
-def oracle_engine(monkeypatch):
+@pytest.fixture(autouse=True, params=["native", "python"])
+def oracle_engine(monkeypatch, request):
+    """both host paths: the native tokenise/filter/dedup pass (csrc/host_parse.cpp) and the Python functions"""
+    monkeypatch.setenv("BREAKFAST_B200_HOST", request.param)
     OracleEngine.install(monkeypatch)
 
 
