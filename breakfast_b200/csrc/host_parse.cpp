@@ -13,6 +13,9 @@
 //      strictly binary CSR the device wants (repeats thermometer-coded, columns ascending), and the
 //      filtered strings.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -77,9 +80,14 @@ struct State {
     int32_t n_vocab = 0, n_cols = 0;
 };
 
-struct VecHash {
+struct VecHash {  // word-wise mix over the token ids of a profile
     size_t operator()(const std::pair<const int32_t*, size_t>& k) const {
-        return (size_t)hash_bytes(reinterpret_cast<const char*>(k.first), k.second * sizeof(int32_t));
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ k.second;
+        for (size_t i = 0; i < k.second; ++i) {
+            h ^= (uint64_t)(uint32_t)k.first[i] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+            h *= 0xff51afd7ed558ccdull;
+        }
+        return (size_t)(h ^ (h >> 32));
     }
 };
 struct VecEq {
@@ -146,6 +154,14 @@ void bfh_get_distinct(void* h, char* bytes, int64_t* offsets) {
 // matrix; empty tokens never enter the matrix (breakfast.py:208-209).
 int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
     State* st = static_cast<State*>(h);
+    const bool timing = getenv("BFH_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bfh_build] %s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     const int64_t n = st->n_seq;
     const int32_t n_distinct = (int32_t)st->tokens.off.size();
     std::vector<uint8_t> is_empty((size_t)n_distinct);
@@ -166,6 +182,7 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
         }
         kept_ptr[r + 1] = (int64_t)kept.size();
     }
+    lap("filter");
     // dedup in first-appearance order
     std::vector<int64_t> uniq_rows;
     if (filter_active) {
@@ -191,12 +208,15 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
             st->codes[r] = id;
         }
     }
+    lap("dedup");
     const int64_t nu = (int64_t)uniq_rows.size();
     st->first_seq.resize((size_t)nu);
     // token CSR of the unique profiles, vocabulary by first appearance (breakfast.py:199-213)
     std::vector<int32_t> vocab_of((size_t)n_distinct, -1);
     st->u_ptr.assign((size_t)nu + 1, 0);
     st->s_off.assign((size_t)nu + 1, 0);
+    st->u_idx.reserve(kept.size());
+    st->s_bytes.reserve(kept.size() * 8);
     for (int64_t u = 0; u < nu; ++u) {
         const int64_t r = uniq_rows[u];
         st->first_seq[u] = (int32_t)r;
@@ -218,6 +238,7 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
         }
         st->s_off[u + 1] = (int64_t)st->s_bytes.size();
     }
+    lap("token csr + strings");
     // strictly binary rows: k-th repeat (k >= 1) of a token inside a profile becomes its own column
     std::unordered_map<int64_t, int32_t> extra;
     st->n_cols = st->n_vocab;
@@ -245,6 +266,7 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
         if (has_extra) std::sort(st->b_idx.begin() + (int64_t)base, st->b_idx.end());
         st->b_ptr[u + 1] = (int64_t)st->b_idx.size();
     }
+    lap("binary csr");
     st->buf = nullptr;
     return 0;
 }
