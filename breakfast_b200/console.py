@@ -39,6 +39,8 @@ def _options():
         (("--skip-del/--no-skip-del",), dict(default=True, help="Ignore deletions")),
         (("--skip-ins/--no-skip-ins",), dict(default=True, help="Ignore insertions")),
         (("--jobs",), dict(type=click.IntRange(1), default=1, envvar="OMP_NUM_THREADS", help="Host threads (kept for compatibility; the distance work runs on the GPU)")),
+        # not in the reference: how many GPUs of this box share the pairwise work (default 1)
+        (("--gpus",), dict(type=click.IntRange(1), default=1, help="GPUs to partition the pairwise work over")),
     ]
     return [click.Option(list(names), **kw) for names, kw in spec]
 
@@ -48,7 +50,9 @@ def _explicit(ctx, name, *sources_that_do_not_count):
 
 
 def run(input_file, outdir, input_cache, output_cache, id_col, clust_col, var_type, sep, sep2, max_dist,
-        min_cluster_size, trim_start, trim_end, reference_length, skip_del, skip_ins, jobs):
+        min_cluster_size, trim_start, trim_end, reference_length, skip_del, skip_ins, jobs, gpus=1):
+    if gpus > 1 and not os.environ.get("BREAKFAST_B200_DEVICES"):
+        os.environ["BREAKFAST_B200_DEVICES"] = ",".join(str(d) for d in range(gpus))
     if var_type not in DNA_TYPES:
         # trimming / indel skipping only make sense for nucleotide positions: the DNA-oriented
         # defaults are dropped silently, an explicit request is an error

@@ -23,6 +23,14 @@ def default_engine() -> str:
     return os.environ.get("BREAKFAST_B200_ENGINE", "sketch")
 
 
+def default_devices() -> list:
+    """Devices for one job: BREAKFAST_B200_DEVICES="0,1,2,3" (or --gpus N on the CLI); default = one device."""
+    spec = os.environ.get("BREAKFAST_B200_DEVICES", "")
+    if spec.strip():
+        return [int(x) for x in spec.split(",") if x.strip() != ""]
+    return [default_device()]
+
+
 def _context_options() -> dict:
     opts = {}
     if "BREAKFAST_B200_SKETCH_BITS" in os.environ:
@@ -91,11 +99,64 @@ class ClusterResult:
     edges: tuple | None = None               # (src, dst) int32, src < dst, when requested
 
 
+def _components_multi_device(indptr, indices, n_cols, max_dist, devices, want_edges, engine, query_rows=None,
+                             lists=None) -> ClusterResult:
+    """Single-process multi-GPU: one host thread and one context per device, the band work items dealt
+    cyclically (rank r of len(devices)), labels merged on the first device (union(i, labels_r[i]))."""
+    import threading
+    world = len(devices)
+    ctxs, stats, labels, edges, errors = [None] * world, [None] * world, [None] * world, [None] * world, []
+
+    def work(r):
+        try:
+            ctx = _native.Context(device=devices[r], engine=engine, want_edges=int(bool(want_edges)), **_context_options())
+            ctxs[r] = ctx
+            ctx.upload_csr(indptr, indices, n_cols, query_rows=query_rows)
+            stats[r] = ctx.run_sync(max_dist, rank=r, world=world)
+            labels[r] = ctx.download_labels()
+            if want_edges:
+                edges[r] = ctx.download_edges()
+        except BaseException as exc:  # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    try:
+        if errors:
+            raise errors[0]
+        ctx0 = ctxs[0]
+        ctx0.merge_labels_host(np.stack(labels))
+        if lists is not None and len(lists[0]) > 1:
+            ctx0.union_lists(*lists)
+        st = ctx0.sync().as_dict()
+        st["n_edges"] = int(sum(s.n_edges for s in stats))
+        st["n_candidates"] = int(sum(s.n_candidates for s in stats))
+        st["n_gpus"] = world
+        out_labels = ctx0.download_labels()
+        out_edges = None
+        if want_edges:
+            src = np.concatenate([e[0] for e in edges])
+            dst = np.concatenate([e[1] for e in edges])
+            order = np.lexsort((dst, src))
+            out_edges = (src[order], dst[order])
+        return ClusterResult(out_labels, st, out_edges)
+    finally:
+        for ctx in ctxs:
+            if ctx is not None:
+                ctx.close()
+
+
 def components_full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None) -> ClusterResult:
-    """All-pairs run on one GPU: radius-neighbour graph at max_dist + connected components."""
-    device = default_device() if device is None else device
+    """All-pairs run: radius-neighbour graph at max_dist + connected components (one GPU, or all of
+    BREAKFAST_B200_DEVICES with the tile space partitioned over them)."""
     engine = default_engine() if engine is None else engine
     _native.require_device()
+    if device is None and len(default_devices()) > 1:
+        return _components_multi_device(indptr, indices, n_cols, max_dist, default_devices(), want_edges, engine)
+    device = default_device() if device is None else device
     with _native.Context(device=device, engine=engine, want_edges=int(bool(want_edges)), **_context_options()) as ctx:
         ctx.upload_csr(indptr, indices, n_cols)
         st = ctx.run_sync(max_dist)
@@ -108,10 +169,13 @@ def components_incremental(indptr, indices, n_cols, max_dist, new_rows, list_ind
                            want_edges=False, device=None, engine=None) -> ClusterResult:
     """Incremental run: only the new x all block is evaluated (reference: X = new rows, Y = all rows,
     breakfast.py:236-254) and the cached neighbour lists are united on top (breakfast.py:304)."""
-    device = default_device() if device is None else device
     engine = default_engine() if engine is None else engine
     _native.require_device()
     new_rows = np.unique(np.asarray(new_rows, dtype=np.int32))
+    if device is None and len(default_devices()) > 1:
+        return _components_multi_device(indptr, indices, n_cols, max_dist, default_devices(), want_edges, engine,
+                                        query_rows=new_rows, lists=(list_indptr, list_members))
+    device = default_device() if device is None else device
     with _native.Context(device=device, engine=engine, want_edges=int(bool(want_edges)), **_context_options()) as ctx:
         ctx.upload_csr(indptr, indices, n_cols, query_rows=new_rows)
         st = ctx.run_sync(max_dist)

@@ -235,6 +235,36 @@ def test_multi_rank_partition_and_merge(world):
     assert np.array_equal(helpers.merge_labels_cpu(gathered), single)
 
 
+def test_single_process_multi_device_engine(monkeypatch, tmp_path):
+    """the CLI's --gpus path: one host thread + context per device, cyclic work partition, merge on the first
+    device.  With one GPU in the box the same device is listed several times, which exercises the whole path."""
+    from breakfast_b200 import engine
+    indptr, indices, n_cols = synth.generate(8000, seed=17).csr()
+    want, ne = oracle.cluster(indptr, indices, 2)
+    monkeypatch.setenv("BREAKFAST_B200_DEVICES", "0,0,0")
+    res = engine.components_full(indptr, indices, n_cols, 2, want_edges=True)
+    assert np.array_equal(res.labels, want) and res.stats["n_edges"] == ne and res.stats["n_gpus"] == 3
+    ws, wd = oracle.edges(indptr, indices, 2)
+    assert np.array_equal(res.edges[0], ws) and np.array_equal(res.edges[1], wd)
+    # incremental + cached lists over several devices
+    q = np.arange(0, 8000, 9, dtype=np.int32)
+    li, lm = np.array([0, 2, 5], np.int64), np.array([1, 7000, 3, 4, 7999], np.int32)
+    res = engine.components_incremental(indptr, indices, n_cols, 1, q, li, lm, want_edges=True)
+    s1, d1 = oracle.edges(indptr, indices, 1, queries=q)
+    assert np.array_equal(res.edges[0], s1) and np.array_equal(res.edges[1], d1)
+    assert np.array_equal(res.labels, oracle.components(8000, s1, d1, li, lm))
+    # and through the CLI option
+    case = [c for c in helpers.cases("plain") if c["name"] == "syn_dna_d2_m5"][0]
+    monkeypatch.delenv("BREAKFAST_B200_DEVICES")
+    import click.testing
+    from breakfast_b200 import console
+    monkeypatch.setenv("BREAKFAST_B200_DEVICES", "0,0")
+    r = click.testing.CliRunner().invoke(console.main, ["--input-file", str(GOLDEN / case["input"]), "--outdir", str(tmp_path),
+                                                        "--gpus", "2"] + helpers.cli_args(case["opts"]))
+    assert r.exit_code == 0, r.output
+    helpers.assert_matches(case, case["expected"], (tmp_path / "clusters.tsv").read_text())
+
+
 def test_merge_on_device_with_torch_tensors():
     """the torchrun path: labels -> torch device tensor -> (all-gather) -> merge on device"""
     torch = pytest.importorskip("torch")

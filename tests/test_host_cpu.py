@@ -172,7 +172,7 @@ def test_cli_help_lists_every_reference_option(runner):
     for opt in ("--input-file", "--sep", "--outdir", "--max-dist", "--min-cluster-size", "--input-cache",
                 "--output-cache", "--id-col", "--clust-col", "--var-type", "--sep2", "--trim-start", "--trim-end",
                 "--reference-length", "--skip-del", "--no-skip-del", "--skip-ins", "--no-skip-ins", "--jobs",
-                "--version"):
+                "--version", "--gpus"):
         assert opt in res.output, opt
 
 
