@@ -123,7 +123,7 @@ struct bf_ctx {
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
     DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
-    DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, cand, edges, parent, labels, counters, scratch, scratch2;
+    DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, segcnt, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
     // per-run event ring so that bf_sync can report sums over all runs since the last sync
@@ -252,16 +252,16 @@ int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA
     const uint32_t* f8a = (c->has_query ? c->fold8A[0] : c->fold8B[0]).as<uint32_t>();
     const uint4* f8b = c->fold8B[1].as<uint4>();
     k_pairs_l1_imma<<<(unsigned)c->num_sms, PAIR_THREADS, IMMA_SMEM_BYTES, c->stream>>>(
-        f8a, f8b, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, c->rank,
-        c->world, c->queue.as<int2>(), c->queue_cap_used, c->counters.as<DevCounters>());
+        f8a, f8b, nA, nB, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, tri,
+        c->rank, c->world, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(), c->counters.as<DevCounters>());
     CKLC(c);
     CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
-    if (c->K4 == 1)
-        k_pairs_l2<1, true><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
-                                                                  tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
-    else
-        k_pairs_l2<2, true><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
-                                                                  tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
+    const uint4* fa = (c->has_query ? c->foldsA[0] : c->foldsB[0]).as<uint4>();
+    const uint2* fb = c->foldsB[1].as<uint2>();
+    auto l2 = c->K4 == 1 ? k_pairs_l2_unit<1> : k_pairs_l2_unit<2>;
+    l2<<<c->num_sms * L2_SUB, 256, 0, c->stream>>>(A, B, fa, fb, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(),
+                                                  c->num_sms, c->max_dist, tri, c->cand.as<uint2>(), c->cand_cap_used,
+                                                  c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
 }
@@ -391,7 +391,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->wprefix, &c->nwork, &c->items, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -663,6 +663,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         if (c->ran_two_kernel) {
             unsigned long long qcap = c->units_capacity > 0 ? (unsigned long long)c->units_capacity : (1ull << 23);
             TRY(c->queue.ensure((size_t)qcap * sizeof(int2)));
+            TRY(c->segcnt.ensure((size_t)c->num_sms * sizeof(unsigned)));
             c->queue_cap_used = qcap;
         }
     }
@@ -814,8 +815,9 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
                 // level 1: one 32-bit test per pair, half of them by POPC when max_dist is 1 or 2 (the other
                 // half runs POPC-free on the ALU/FMA pipes); level 2: `words` POPC per pair of every queued 32-pair unit
                 st->l2_warp_items = (int64_t)std::min<unsigned long long>(h.n_units, c->queue_cap_used);
-                if (c->level1 == 1) {  // tensor-core level 1: no POPC there
-                    st->popc32_executed = st->l2_warp_items * 32 * words;
+                if (c->level1 == 1) {  // tensor-core level 1: no POPC there; level 2 = the exact 32-bit test of a unit's
+                                       // 32 pairs + `words` POPC for every pair that passes it (counted on the device)
+                    st->popc32_executed = st->l2_warp_items * 32 + (int64_t)h.l2_warp_items * words;
                 } else {
                     const int64_t l1 = (c->max_dist == 1 || c->max_dist == 2) ? st->pairs_evaluated / 2 : st->pairs_evaluated;
                     st->popc32_executed = l1 + st->l2_warp_items * 32 * words;
@@ -862,8 +864,11 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
     c->launches_since_sync = 0;
     if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
         char buf[256];
-        if (h.n_units > c->queue_cap_used) {
-            c->units_capacity = (int64_t)(h.n_units + h.n_units / 4 + 1024);
+        // level1 = 1 cuts the queue into one segment per CTA: the fullest segment decides
+        const unsigned long long seg_need = c->level1 == 1 ? (unsigned long long)h.seg_max * (unsigned long long)c->num_sms : 0;
+        if (h.n_units > c->queue_cap_used || seg_need > c->queue_cap_used) {
+            const unsigned long long need = std::max<unsigned long long>(h.n_units, seg_need);
+            c->units_capacity = (int64_t)(need + need / 4 + 1024 + c->num_sms);
             snprintf(buf, sizeof buf, "level-2 queue overflow: %llu units > capacity %llu; units_capacity raised, run again",
                      (unsigned long long)h.n_units, c->queue_cap_used);
             return fail(BF_ERR_OVERFLOW, buf);

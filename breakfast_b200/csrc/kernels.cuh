@@ -42,7 +42,7 @@ struct DevCounters {
     unsigned long long tilepairs_rank; // tile pairs this rank's level-1 kernel evaluated
     unsigned long long n_units;        // level-2 queue cursor (may exceed capacity -> overflow)
     unsigned int n_comp;
-    unsigned int pad;
+    unsigned int seg_max;              // fullest per-CTA segment of the level-2 pair queue (overflow check)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -289,6 +289,8 @@ __host__ __device__ inline size_t word_offset(int64_t tile, int n_chunks, int K4
 // column-operand order (row = lane + 32 j  ->  lane*4 + j)
 __host__ __device__ inline int fold_pos_a(int row) { return (row & 15) * 8 + (row >> 4); }
 __host__ __device__ inline int fold_pos_b(int row) { return (row & 31) * 4 + (row >> 5); }
+// level-2 unit order of the tensor-core level 1: lane l of a warp holds rows (l/4) + 8 s, s < 16, of the tile
+__host__ __device__ inline int imma_unit_pos(int row) { return (row & 7) * 16 + (row >> 3); }
 
 // 16 bits -> 16 int8 values (+1 for a clear bit, -1 for a set bit)
 __device__ __forceinline__ uint4 expand_pm1(uint32_t bits16) {
@@ -390,8 +392,10 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
             uint32_t f = 0;
 #pragma unroll
             for (int t = 0; t < WORDS; ++t) f ^= w[t];
-            foldA[tile * TILE + fold_pos_a(row)] = f;
-            foldB[tile * TILE + fold_pos_b(row)] = f;
+            // (with the tensor-core level 1 the 32-bit planes feed level 2 only: rows in the order of a level-2
+            // unit = the 16 rows of one accumulator-fragment lane contiguous, columns row-major)
+            foldA[tile * TILE + (fold8b ? imma_unit_pos(row) : fold_pos_a(row))] = f;
+            foldB[tile * TILE + (fold8b ? row : fold_pos_b(row))] = f;
             if (fold8b) {
                 // tensor-core operands: bit k of the fold -> int8 (+1 if clear, -1 if set), so that the int8 dot
                 // product of two rows is 32 - 2 popc(fa xor fb).
@@ -835,6 +839,7 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
 // (accumulator round-trip latency with K = 32, see tools/experiments/l1_tcgen05_kernel.cuh.txt).
 // ------------------------------------------------------------------------------------------
 constexpr int IMMA_STAGES = 6;
+constexpr int L2_SUB = 8;       // CTAs of k_pairs_l2_pair per queue segment
 constexpr int IMMA_TILE_BYTES = TILE * 32;
 constexpr int IMMA_STAGE_BYTES = (1 + L1_GROUP) * IMMA_TILE_BYTES;
 constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
@@ -847,15 +852,22 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], const uint4& a, uint32_t
 }
 
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
-k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ fold8B, const int2* __restrict__ items,
-                unsigned long long items_cap, const unsigned long long* __restrict__ n_work, int max_dist, int rank,
-                int world, int2* __restrict__ queue, unsigned long long queue_cap, DevCounters* __restrict__ counters) {
+k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ fold8B, int64_t nA, int64_t nB,
+                const int2* __restrict__ items, unsigned long long items_cap,
+                const unsigned long long* __restrict__ n_work, int max_dist, int triangular, int rank, int world,
+                int2* __restrict__ queue, unsigned long long queue_cap, unsigned* __restrict__ seg_counts,
+                DevCounters* __restrict__ counters) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + IMMA_STAGES * IMMA_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + IMMA_STAGES;
     int2* meta = reinterpret_cast<int2*>(empty_bar + IMMA_STAGES);
+    __shared__ unsigned seg_cursor;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the level-2 queue is cut into one segment per CTA
+    const unsigned seg_cap = (unsigned)min(queue_cap / gridDim.x, 0xffffffffull);
+    int2* seg = queue + (size_t)blockIdx.x * seg_cap;
     if (threadIdx.x == 0) {
+        seg_cursor = 0;
         for (int s = 0; s < IMMA_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
@@ -939,14 +951,86 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
         }
 #pragma unroll
         for (int jt = 0; jt < L1_GROUP; ++jt) {
-            if (jt < cnt && mxj[jt] >= thr) {  // rare: this thread's 16 x 2 pairs of tile pair (I, J0 + jt) go to level 2
-                const unsigned long long pos = atomicAdd(&counters->n_units, 1ull);
-                if (pos < queue_cap) queue[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+            // rare: one of this lane's 16 x 2 pairs of tile pair (I, J0 + jt) may be within max_dist -> the unit goes
+            // to this CTA's segment of the level-2 queue (shared-memory cursor: no contended global atomic)
+            if (jt < cnt && mxj[jt] >= thr) {
+                const unsigned pos = atomicAdd(&seg_cursor, 1u);
+                if (pos < seg_cap) seg[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(PAIR_CONSUMER_WARPS * 32) : "memory");   // consumer warps only
+    if (threadIdx.x == 0) {
+        const unsigned n = seg_cursor;
+        seg_counts[blockIdx.x] = n;
+        if (n) {
+            atomicAdd(&counters->n_units, (unsigned long long)n);
+            atomicMax(&counters->seg_max, n);
+        }
+    }
+}
+
+// level 2 of the tensor-core level 1: one THREAD per queued unit = the 16 x 2 pairs (rows (tx/4) + 8 s of tile I,
+// columns 8 ty + 2 (tx%4) + {0, 1} of tile J) held by one accumulator-fragment lane.  The unit's 16 + 2 32-bit
+// folds are three contiguous loads (unit-order planes written by the pack kernel); only the pairs that pass the
+// exact 32-bit test (about one in sixty) fetch the two full sketches.
+template <int K4>
+__global__ void __launch_bounds__(256)
+k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, const uint4* __restrict__ foldA,
+                const uint2* __restrict__ foldB, int64_t nA, int64_t nB, const int2* __restrict__ queue,
+                unsigned long long queue_cap, const unsigned* __restrict__ seg_counts, int n_segs, int threshold,
+                int triangular, uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    // blockIdx.x = segment * L2_SUB + slice: the CTAs of one segment stride over its units
+    const unsigned seg_cap = (unsigned)min(queue_cap / (unsigned)n_segs, 0xffffffffull);
+    const int sgm = blockIdx.x / L2_SUB, sub = blockIdx.x % L2_SUB;
+    const unsigned n = min(__ldg(&seg_counts[sgm]), seg_cap);
+    const int2* seg = queue + (size_t)sgm * seg_cap;
+    unsigned full_checks = 0;
+    for (unsigned u = sub * blockDim.x + threadIdx.x; u < n; u += L2_SUB * blockDim.x) {
+        const int2 unit = __ldg(&seg[u]);
+        const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
+        const int r0 = tx >> 2, c0 = 8 * ty + 2 * (tx & 3);
+        const uint2 fb = __ldg(&foldB[((size_t)J * TILE + c0) >> 1]);
+        const uint4* fa4 = foldA + ((size_t)I * TILE + r0 * 16) / 4;
+        const int64_t gi0 = (int64_t)I * TILE + r0, gj0 = (int64_t)J * TILE + c0;
+        // pass 1, no loads beyond the folds: bit 2 s + j = pair (row r0 + 8 s, column c0 + j) passes the 32-bit test
+        uint32_t hits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 fa = __ldg(&fa4[q]);
+            const uint32_t f[4] = {fa.x, fa.y, fa.z, fa.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                hits |= (__popc(f[t] ^ fb.x) <= threshold ? 1u : 0u) << (2 * (4 * q + t));
+                hits |= (__popc(f[t] ^ fb.y) <= threshold ? 2u : 0u) << (2 * (4 * q + t));
+            }
+        }
+        // pass 2: the lanes of a warp walk their own survivors together (one or two rounds, whatever the slots)
+        while (hits) {
+            const int bit = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int s = bit >> 1, j = bit & 1;
+            const int64_t gi = gi0 + 8 * s, gj = gj0 + j;
+            if (gi >= nA || gj >= nB || (triangular && gi >= gj)) continue;
+            ++full_checks;
+            const uint4* a = bitsA + (size_t)I * (K4 * TILE) + (r0 + 8 * s);
+            const uint4* b = bitsB + (size_t)J * (K4 * TILE) + (c0 + j);
+            int d = 0;
+#pragma unroll
+            for (int k4 = 0; k4 < K4; ++k4) {
+                const uint4 x = __ldg(&a[k4 * TILE]), y = __ldg(&b[k4 * TILE]);
+                d += __popc(x.x ^ y.x) + __popc(x.y ^ y.y) + __popc(x.z ^ y.z) + __popc(x.w ^ y.w);
+            }
+            if (d <= threshold) {
+                const unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
+                if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
+            }
+        }
+    }
+    full_checks = __reduce_add_sync(0xffffffffu, full_checks);
+    if ((threadIdx.x & 31) == 0 && full_checks) atomicAdd(&counters->l2_warp_items, (unsigned long long)full_checks);
 }
 
 // UNIT_IMMA = false: unit = the 8 x 4 pairs (ty + 16 i, tx + 32 j) of a k_pairs_l1 thread

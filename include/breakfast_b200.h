@@ -78,8 +78,9 @@ typedef struct bf_stats {
     double ms_pairs_sum;      /* summed device time of the pair kernel (CUDA events, own stream) */
     double ms_total_sum;      /* summed device time of whole passes                            */
     /* pair kernel work of the last run on this rank */
-    int64_t l2_warp_items;    /* units that needed the full-width pass: 32-pair thread units (two-kernel path,
-                                 128/256-bit sketches) or 1024-pair warp units (single-kernel two-level path) */
+    int64_t l2_warp_items;    /* units level 1 handed to level 2: 32-pair thread units (two-kernel forms; with the
+                                 tensor-core level 1 only the pairs passing the 32-bit test are read at full width)
+                                 or 1024-pair warp units (single-kernel form)                                     */
     int64_t popc32_executed;  /* POPC32 lane-ops the pair kernel executed: level 1 + level 2       */
     double ms_l1_sum;         /* summed device time of the level-1 kernel (two-kernel path), like ms_pairs_sum */
 } bf_stats;
