@@ -150,7 +150,7 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
         TRY(keys[i].ensure(n * sizeof(uint32_t)));
         TRY(vals[i].ensure(n * sizeof(int32_t)));
     }
-    TRY(c->sort_counts.ensure((size_t)256 * nblocks * sizeof(uint32_t)));
+    TRY(c->sort_counts.ensure((size_t)256 * (nblocks + 1) * sizeof(uint32_t)));
     TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
     uint32_t* max_key = c->sort_max.as<uint32_t>() + side;
     CK(cudaMemsetAsync(max_key, 0, sizeof(uint32_t), c->stream));
@@ -162,11 +162,11 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], 
         k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
                                                     c->sort_counts.as<uint32_t>(), nblocks, max_key);
         CKLC(c);
-        k_exclusive_scan<uint32_t><<<1, 1024, 0, c->stream>>>(c->sort_counts.as<uint32_t>(),
-                                                              (int64_t)256 * nblocks, nullptr, max_key, shift);
+        uint32_t* totals = c->sort_counts.as<uint32_t>() + (size_t)256 * nblocks;
+        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, shift, max_key);
         CKLC(c);
         k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
-                                                       c->sort_counts.as<uint32_t>(), nblocks,
+                                                       c->sort_counts.as<uint32_t>(), totals, nblocks,
                                                        keys[out].as<uint32_t>(), vals[out].as<int32_t>(), max_key);
         CKLC(c);
     }
@@ -190,10 +190,12 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
                 f8a = fold8[0].as<uint32_t>();
                 f8b = fold8[1].as<uint4>();
             }
-            if (c->sketch_bits == 128)
-                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>(), f8a, f8b);
-            else
-                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, bits.as<uint32_t>(), folds[0].as<uint32_t>(), folds[1].as<uint32_t>(), f8a, f8b);
+            uint32_t *b32 = bits.as<uint32_t>(), *fo0 = folds[0].as<uint32_t>(), *fo1 = folds[1].as<uint32_t>();
+            if (c->sketch_bits == 128) {
+                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, b32, fo0, fo1, f8a, f8b);
+            } else {
+                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, b32, fo0, fo1, f8a, f8b);
+            }
         } else {
             const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
             k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
@@ -304,11 +306,9 @@ int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int
 int finish_labels(bf_ctx* c) {
     const int64_t n = c->n_rows;
     if (n == 0) return BF_OK;
-    k_uf_labels<<<grid_for(n, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n, c->labels.as<int32_t>());
-    CKLC(c);
     CK(cudaMemsetAsync(&c->counters.as<DevCounters>()->n_comp, 0, sizeof(unsigned int), c->stream));
-    k_count_roots<<<grid_for(n, 256), 256, 0, c->stream>>>(c->labels.as<int32_t>(), n,
-                                                           &c->counters.as<DevCounters>()->n_comp);
+    k_uf_labels<<<grid_for(n, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n, c->labels.as<int32_t>(),
+                                                         &c->counters.as<DevCounters>()->n_comp);
     CKLC(c);
     return BF_OK;
 }

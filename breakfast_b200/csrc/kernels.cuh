@@ -65,7 +65,7 @@ __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* _
     if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(max_key, k);
 }
 
-// One radix pass = k_sort_hist -> k_exclusive_scan -> k_sort_scatter.  A block owns SORT_ITEMS
+// One radix pass = k_sort_hist -> k_sort_scan_digits -> k_sort_scatter.  A block owns SORT_ITEMS
 // consecutive rows, warp w of it the w-th eighth; every warp keeps a private 256-bin histogram in
 // shared memory (no atomics: __match_any_sync groups equal digits, the group leader adds the group
 // size), so ranks are reproducible and the pass is stable.
@@ -101,9 +101,35 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ 
     counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = c;
 }
 
+// Scan step of a radix pass: one warp per digit turns its row of counts[digit][block] into exclusive prefixes
+// over the blocks (in place) and leaves the digit's total in totals[digit]; k_sort_scatter adds the exclusive
+// scan over the 256 digit totals itself.
+__global__ void __launch_bounds__(256) k_sort_scan_digits(uint32_t* __restrict__ counts, int nblocks,
+                                                          uint32_t* __restrict__ totals, int shift,
+                                                          const uint32_t* __restrict__ max_key) {
+    if ((*max_key >> shift) == 0) return;
+    const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t* row = counts + (size_t)d * nblocks;
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += 32) {
+        const int b = b0 + lane;
+        const uint32_t v = b < nblocks ? row[b] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (b < nblocks) row[b] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) totals[d] = carry;
+}
+
 __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys,
                                                       const int32_t* __restrict__ vals, int64_t n, int shift,
-                                                      const uint32_t* __restrict__ offsets, int nblocks,
+                                                      const uint32_t* __restrict__ offsets,
+                                                      const uint32_t* __restrict__ totals, int nblocks,
                                                       uint32_t* __restrict__ keys_out,
                                                       int32_t* __restrict__ vals_out,
                                                       const uint32_t* __restrict__ max_key) {
@@ -123,8 +149,25 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     const int64_t wbase = base + warp * SORT_PER_WARP;
     sort_warp_count(keys, n, shift, wbase, whist[warp], lane);
     __syncthreads();
+    __shared__ uint32_t wsum[SORT_WARPS];
+    uint32_t digit_base;   // exclusive scan over the 256 digit totals (thread = digit)
+    {
+        const uint32_t t = totals[threadIdx.x];
+        uint32_t x = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) before += w < warp ? wsum[w] : 0u;
+        digit_base = before + x - t;
+    }
     {   // digit d: global start of the block + exclusive prefix over the warps of the block
-        uint32_t run = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+        uint32_t run = digit_base + offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             const uint32_t c = whist[w][threadIdx.x];
@@ -345,9 +388,56 @@ __global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__
     for (int i = threadIdx.x; i < words_per_tile / 4; i += 256) dst[i] = src[i];
 }
 
-// SKETCH, m = 32*WORDS <= 256 bits: no shared memory and no atomics.  A warp folds one row at a time:
-// every lane XORs its columns' bits into WORDS registers, redux.sync.xor combines the lanes, lane 0
-// stores the row's 16-byte groups.  HBM-bound: reads 4*nnz + 12*N bytes, writes N*m/8 bytes.
+// Stores of one packed row (128/256-bit sketches) at slot `row` of sorted tile `tile`: the sketch itself, its
+// 32-bit fold in the two level-1/level-2 plane orders and, for the tensor-core level 1, the +-1 expanded fold.
+template <int WORDS>
+__device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64_t tile, int row, uint32_t* __restrict__ bits,
+                                               uint32_t* __restrict__ foldA, uint32_t* __restrict__ foldB,
+                                               uint32_t* __restrict__ fold8a, uint4* __restrict__ fold8b) {
+    constexpr int K4 = WORDS / 4;
+    uint4* dst = reinterpret_cast<uint4*>(bits) + (size_t)tile * (K4 * TILE);
+#pragma unroll
+    for (int g = 0; g < K4; ++g) dst[g * TILE + row] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    // level-1 operand: the sketch folded once more to 32 bits, stored twice so that both the
+    // row-operand (8 rows of a warp contiguous) and the column-operand (4 rows of a lane
+    // contiguous) of k_pairs_l1 are single 128-bit shared loads
+    uint32_t f = 0;
+#pragma unroll
+    for (int t = 0; t < WORDS; ++t) f ^= w[t];
+    // (with the tensor-core level 1 the 32-bit planes feed level 2 only: rows in the order of a level-2
+    // unit = the 16 rows of one accumulator-fragment lane contiguous, columns row-major)
+    foldA[tile * TILE + (fold8b ? imma_unit_pos(row) : fold_pos_a(row))] = f;
+    foldB[tile * TILE + (fold8b ? row : fold_pos_b(row))] = f;
+    if (fold8b) {
+        // tensor-core operands: bit k of the fold -> int8 (+1 if clear, -1 if set), so that the int8 dot
+        // product of two rows is 32 - 2 popc(fa xor fb).
+        //  column operand: plain row-major, 32 bytes per row (a lane's B fragment = 8 contiguous bytes)
+        //  row operand: m16n8k32 A-fragment order - the 16 bytes {row r: k lo, row r+8: k lo, row r: k hi,
+        //  row r+8: k hi} of lane (r%8)*4 + s4 of m-tile r/16 are contiguous, so a fragment is one LDS.128
+        const uint4 e0 = expand_pm1(f & 0xffffu), e1 = expand_pm1(f >> 16);
+        uint4* tb = fold8b + (size_t)tile * (TILE * 2);
+        tb[row * 2 + 0] = e0;
+        tb[row * 2 + 1] = e1;
+        uint32_t* ta = fold8a + (size_t)tile * (TILE * 8);
+        const int m = row >> 4, h = (row >> 3) & 1, fr = row & 7;
+        const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};   // bytes 4q .. 4q+3
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            uint32_t* frag = ta + ((m * 8 + fr) * 4 + s4) * 4;
+            frag[h] = words[2 * s4];           // k lo of lane (fr * 4 + s4)'s slice (bytes 8 s4 .. 8 s4 + 3)
+            frag[2 + h] = words[2 * s4 + 1];   // k hi (bytes 8 s4 + 4 .. 8 s4 + 7)
+        }
+    }
+}
+
+// SKETCH, m = 32*WORDS <= 256 bits.  A block builds one sorted tile (128 rows).  Rows are short (about 90 columns),
+// so a warp folds FOUR rows at a time, eight lanes each: every lane XORs the bits of its columns straight into the
+// row's sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction), four loads per
+// lane in flight.  Afterwards thread t stores row t: all 128 rows of the tile at once, coalesced.
+// Reads 4*nnz + 12*N bytes, writes N*(m/8 + 8 [+ 64]) bytes.
+// (Measured alternatives at 1 M rows of ~89 columns: a warp per row with per-lane word selects + redux.sync and
+// lane-0 stores: 0.34 ms; the same reading the CSR in storage order and scattering the outputs: 0.34 ms - the
+// gather is not the limit; a thread per row: 0.69 ms, its 32-sector loads are L1-wavefront bound; this: 0.13 ms.)
 template <int WORDS>
 __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restrict__ indptr,
                                                          const int32_t* __restrict__ indices,
@@ -355,68 +445,49 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
                                                          uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
                                                          uint32_t* __restrict__ foldB, uint32_t* __restrict__ fold8a,
                                                          uint4* __restrict__ fold8b) {
-    constexpr int K4 = WORDS / 4;
+    __shared__ uint32_t sk[TILE][WORDS];
+    __shared__ int64_t row_b[TILE], row_e[TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
-    int64_t my_b = 0, my_e = 0;
-    if (lane < TILE / 8) {
-        const int64_t p = tile * TILE + warp + 8 * lane;
+    if (threadIdx.x < TILE) {
+        const int64_t p = tile * TILE + threadIdx.x;
+        int64_t b = 0, e = 0;   // rows past n stay all-zero (never emitted: index check in the pair kernels)
         if (p < n) {
             const int32_t r = perm[p];
-            my_b = indptr[r];
-            my_e = indptr[r + 1];
+            b = indptr[r];
+            e = indptr[r + 1];
         }
+        row_b[threadIdx.x] = b;
+        row_e[threadIdx.x] = e;
+#pragma unroll
+        for (int t = 0; t < WORDS; ++t) sk[threadIdx.x][t] = 0u;
     }
-    uint4* dst = reinterpret_cast<uint4*>(bits) + (size_t)tile * (K4 * TILE);
-#pragma unroll 8
-    for (int k = 0; k < TILE / 8; ++k) {
-        const int64_t b = __shfl_sync(0xffffffffu, my_b, k), e = __shfl_sync(0xffffffffu, my_e, k);
-        uint32_t w[WORDS];
+    __syncthreads();
+    const int sub = lane >> 3, l8 = lane & 7;
+#pragma unroll 1
+    for (int k = 0; k < TILE / 32; ++k) {
+        const int row = warp * (TILE / 8) + 4 * k + sub;
+        const int64_t e = row_e[row];
+        uint32_t* dst = sk[row];
+        for (int64_t q = row_b[row] + l8; q < e; q += 32) {
+            int32_t col[4];
 #pragma unroll
-        for (int t = 0; t < WORDS; ++t) w[t] = 0u;
-        for (int64_t q = b + lane; q < e; q += 32) {
-            const uint32_t h = fold_hash((uint32_t)__ldg(&indices[q]), log2m);
-            const uint32_t bit = 1u << (h & 31), word = h >> 5;
+            for (int t = 0; t < 4; ++t) col[t] = q + 8 * t < e ? __ldg(&indices[q + 8 * t]) : -1;
 #pragma unroll
-            for (int t = 0; t < WORDS; ++t) w[t] ^= (word == (uint32_t)t) ? bit : 0u;
-        }
-#pragma unroll
-        for (int t = 0; t < WORDS; ++t) w[t] = __reduce_xor_sync(0xffffffffu, w[t]);
-        if (lane == 0) {
-            const int row = warp + 8 * k;  // rows past n stay all-zero (never emitted: index check in k_pairs)
-#pragma unroll
-            for (int g = 0; g < K4; ++g) dst[g * TILE + row] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
-            // level-1 operand: the sketch folded once more to 32 bits, stored twice so that both the
-            // row-operand (8 rows of a warp contiguous) and the column-operand (4 rows of a lane
-            // contiguous) of k_pairs_l1 are single 128-bit shared loads
-            uint32_t f = 0;
-#pragma unroll
-            for (int t = 0; t < WORDS; ++t) f ^= w[t];
-            // (with the tensor-core level 1 the 32-bit planes feed level 2 only: rows in the order of a level-2
-            // unit = the 16 rows of one accumulator-fragment lane contiguous, columns row-major)
-            foldA[tile * TILE + (fold8b ? imma_unit_pos(row) : fold_pos_a(row))] = f;
-            foldB[tile * TILE + (fold8b ? row : fold_pos_b(row))] = f;
-            if (fold8b) {
-                // tensor-core operands: bit k of the fold -> int8 (+1 if clear, -1 if set), so that the int8 dot
-                // product of two rows is 32 - 2 popc(fa xor fb).
-                //  column operand: plain row-major, 32 bytes per row (a lane's B fragment = 8 contiguous bytes)
-                //  row operand: m16n8k32 A-fragment order - the 16 bytes {row r: k lo, row r+8: k lo, row r: k hi,
-                //  row r+8: k hi} of lane (r%8)*4 + w of m-tile r/16 are contiguous, so a fragment is one LDS.128
-                const uint4 e0 = expand_pm1(f & 0xffffu), e1 = expand_pm1(f >> 16);
-                uint4* tb = fold8b + (size_t)tile * (TILE * 2);
-                tb[row * 2 + 0] = e0;
-                tb[row * 2 + 1] = e1;
-                uint32_t* ta = fold8a + (size_t)tile * (TILE * 8);
-                const int m = row >> 4, h = (row >> 3) & 1, fr = row & 7;
-                const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};   // bytes 4q .. 4q+3
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    uint32_t* frag = ta + ((m * 8 + fr) * 4 + w) * 4;
-                    frag[h] = words[2 * w];           // k lo of this lane's slice (bytes 8w .. 8w+3)
-                    frag[2 + h] = words[2 * w + 1];   // k hi (bytes 8w+4 .. 8w+7)
+            for (int t = 0; t < 4; ++t) {
+                if (col[t] >= 0) {   // column ids are non-negative
+                    const uint32_t h = fold_hash((uint32_t)col[t], log2m);
+                    atomicXor(&dst[h >> 5], 1u << (h & 31));
                 }
             }
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE) {
+        uint32_t w[WORDS];
+#pragma unroll
+        for (int t = 0; t < WORDS; ++t) w[t] = sk[threadIdx.x][t];
+        pack_store_row<WORDS>(w, tile, threadIdx.x, bits, foldA, foldB, fold8a, fold8b);
     }
 }
 
@@ -1119,17 +1190,18 @@ __global__ void k_uf_init(int* __restrict__ parent, int64_t n) {
     if (i < n) parent[i] = (int)i;
 }
 
-__global__ void k_uf_labels(int* __restrict__ parent, int64_t n, int32_t* __restrict__ labels) {
+// labels[i] = root of i (= smallest row of its component); *n_roots += rows that are their own root
+__global__ void __launch_bounds__(256) k_uf_labels(int* __restrict__ parent, int64_t n, int32_t* __restrict__ labels,
+                                                   unsigned int* __restrict__ n_roots) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) labels[i] = uf_find(parent, (int)i);
-}
-
-__global__ void __launch_bounds__(256) k_count_roots(const int32_t* __restrict__ labels, int64_t n,
-                                                     unsigned int* __restrict__ out) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    unsigned int is_root = (i < n && labels[i] == (int32_t)i) ? 1u : 0u;
-    unsigned int m = __ballot_sync(0xffffffffu, is_root);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned int)__popc(m));
+    bool is_root = false;
+    if (i < n) {
+        const int r = uf_find(parent, (int)i);
+        labels[i] = r;
+        is_root = r == (int)i;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, is_root);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_roots, (unsigned int)__popc(m));
 }
 
 __global__ void k_uf_edges(int* __restrict__ parent, const int32_t* __restrict__ src,
@@ -1217,29 +1289,42 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                     // differ by at most max_dist in the two rows (at most that many one-sided columns
                     // precede it), so matching A[k] against B[k-d..k+d] finds every common column; if the
                     // distance is larger the count can only be too small, i.e. the pair is still rejected.
-                    // No data-dependent addressing: all loads of a sweep are independent and coalesced.
-                    if constexpr (DWIN > 0) {
-                        // compile-time window and four predicated sweeps (rows up to 128 columns): every load
-                        // of a candidate is independent of the others and issued back to back, so a candidate
-                        // costs about one memory round trip; longer rows continue in the loop below.
-                        // (Four candidates per warp in 8-lane groups was tried: slower, the kernel is bound by
-                        // the scattered 360-byte row reads, ~545 MB per pass, not by latency.)
-                        auto match_at = [&](int64_t k) {
-                            const int x = __ldg(&indices[ia + k]);
-                            bool hit = false;
+                    // No data-dependent addressing.
+                    if (DWIN > 0 && lb <= 4 * 32) {
+                        // Rows of up to 128 columns (nearly all): each lane loads its <= 4 columns of either row once
+                        // (positions lane + 32 s; all eight loads independent and issued back to back, so a candidate
+                        // costs about one memory round trip) and gets the +-DWIN neighbours of B from lane rotations
+                        // instead of more loads - the kernel is bound by issued instructions, not by bytes.
+                        const int32_t* pa = indices + ia;
+                        const int32_t* pb = indices + ib;
+                        const int la32 = (int)la, lb32 = (int)lb;
+                        int av[4], bv[4];
 #pragma unroll
-                            for (int o = -DWIN; o <= DWIN; ++o) {
-                                const int64_t j = k + o;
-                                if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
-                            }
-                            return hit ? 1 : 0;
-                        };
-#pragma unroll
-                        for (int sweep = 0; sweep < 4; ++sweep) {
-                            const int64_t k = lane + 32 * sweep;
-                            if (k < la) inter += match_at(k);
+                        for (int sw = 0; sw < 4; ++sw) {
+                            const int k = lane + 32 * sw;
+                            av[sw] = k < la32 ? __ldg(pa + k) : -2;   // column ids are >= 0: the fillers match nothing
+                            bv[sw] = k < lb32 ? __ldg(pb + k) : -1;
                         }
-                        for (int64_t k = lane + 128; k < la; k += 32) inter += match_at(k);
+                        constexpr int NW = DWIN > 0 ? DWIN : 1;
+                        int dn[4][NW], up[4][NW];   // bv[sw] rotated by -o / +o lanes
+#pragma unroll
+                        for (int sw = 0; sw < 4; ++sw)
+#pragma unroll
+                            for (int o = 1; o <= NW; ++o) {
+                                dn[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane - o) & 31);
+                                up[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane + o) & 31);
+                            }
+#pragma unroll
+                        for (int sw = 0; sw < 4; ++sw) {
+                            bool hit = av[sw] == bv[sw];
+#pragma unroll
+                            for (int o = 1; o <= NW; ++o) {
+                                const int below = lane >= o ? dn[sw][o - 1] : (sw > 0 ? dn[sw - 1][o - 1] : -1);        // B[k - o]
+                                const int above = lane + o < 32 ? up[sw][o - 1] : (sw < 3 ? up[sw + 1][o - 1] : -1);   // B[k + o]
+                                hit |= (av[sw] == below) | (av[sw] == above);
+                            }
+                            inter += hit ? 1 : 0;
+                        }
                     } else {
                         for (int64_t k = lane; k < la; k += 32) {
                             const int x = __ldg(&indices[ia + k]);
