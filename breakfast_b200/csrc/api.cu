@@ -107,6 +107,8 @@ struct bf_ctx {
     int K4 = 1, n_chunks = 1;
     int64_t bits_per_row = 0, tilesA = 0, tilesB = 0;
     unsigned long long cand_cap_used = 0, items_cap_used = 0;
+    int64_t sched_entries = 0;   // schedule entries of the last run = row tiles * sched_ranges
+    int sched_ranges = 1;
     bool ran_two_level = false, ran_two_kernel = false;
     unsigned long long queue_cap_used = 0;
     float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
@@ -122,7 +124,7 @@ struct bf_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
-    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max;
+    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max, sk_rows;
     DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, segcnt, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
@@ -143,33 +145,69 @@ int set_device(bf_ctx* c) {
 }
 
 // rows sorted by (clamped) cardinality: keys[0]/vals[0] hold the result (two ping-pong passes)
-int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2], int side) {
+// Stable LSD radix sort of (key, row) by the 32-bit composite key (kernels.cuh, K2): four 8-bit passes, of which
+// those whose digit is zero in every key degenerate to a copy (decided on the device from the OR of the keys).
+// keys_ready: keys[0] / vals[0] and the OR word of `side` were already written (k_pack_sketch_rows, k_gather_keys).
+int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2], int side, bool keys_ready) {
     if (n == 0) return BF_OK;
     const int nblocks = (int)ceil_div(n, SORT_ITEMS);
-    for (int i = 0; i < 2; ++i) {
-        TRY(keys[i].ensure(n * sizeof(uint32_t)));
-        TRY(vals[i].ensure(n * sizeof(int32_t)));
-    }
     TRY(c->sort_counts.ensure((size_t)256 * (nblocks + 1) * sizeof(uint32_t)));
-    TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
-    uint32_t* max_key = c->sort_max.as<uint32_t>() + side;
-    CK(cudaMemsetAsync(max_key, 0, sizeof(uint32_t), c->stream));
-    k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_indptr, rows_dev, n,
-                                                          keys[0].as<uint32_t>(), vals[0].as<int32_t>(), max_key);
-    CKLC(c);
-    for (int pass = 0; pass < 2; ++pass) {
+    uint32_t* or_key = c->sort_max.as<uint32_t>() + side;
+    if (!keys_ready) {
+        CK(cudaMemsetAsync(or_key, 0, sizeof(uint32_t), c->stream));
+        k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_indptr, rows_dev, n,
+                                                              keys[0].as<uint32_t>(), vals[0].as<int32_t>(), or_key);
+        CKLC(c);
+    }
+    for (int pass = 0; pass < 4; ++pass) {
         const int in = pass & 1, out = in ^ 1, shift = 8 * pass;
         k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
-                                                    c->sort_counts.as<uint32_t>(), nblocks, max_key);
+                                                    c->sort_counts.as<uint32_t>(), nblocks, or_key);
         CKLC(c);
         uint32_t* totals = c->sort_counts.as<uint32_t>() + (size_t)256 * nblocks;
-        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, shift, max_key);
+        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, shift, or_key);
         CKLC(c);
         k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
                                                        c->sort_counts.as<uint32_t>(), totals, nblocks,
-                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>(), max_key);
+                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>(), or_key);
         CKLC(c);
     }
+    return BF_OK;
+}
+
+int ensure_sort_buffers(bf_ctx* c, int64_t n, DevBuf keys[2], DevBuf vals[2]) {
+    for (int i = 0; i < 2; ++i) {
+        TRY(keys[i].ensure(std::max<int64_t>(n, 1) * sizeof(uint32_t)));
+        TRY(vals[i].ensure(std::max<int64_t>(n, 1) * sizeof(int32_t)));
+    }
+    TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
+    return BF_OK;
+}
+
+// 128/256-bit sketches (kernels.cuh K1): do the rows of a side go through the staged two-step pack?
+inline bool staged_pack(const bf_ctx* c) {
+    return c->engine == BF_ENGINE_SKETCH && (c->sketch_bits == 128 || c->sketch_bits == 256);
+}
+
+// step 1 of the staged pack: sketches + sort keys of ALL rows of the matrix in storage order (the B side is the
+// whole matrix; a query subset reads its rows' sketches and keys from the same staging arrays)
+int pack_stage_all_rows(bf_ctx* c) {
+    const int64_t n = c->n_rows;
+    if (n == 0) return BF_OK;
+    int log2m = 0;
+    while ((1 << log2m) < c->sketch_bits) ++log2m;
+    const int words = c->sketch_bits / 32;
+    TRY(c->sk_rows.ensure((size_t)n * words * sizeof(uint32_t)));
+    uint32_t* or_key = c->sort_max.as<uint32_t>();
+    CK(cudaMemsetAsync(or_key, 0, 2 * sizeof(uint32_t), c->stream));
+    const unsigned blocks = (unsigned)ceil_div(n, TILE);
+    if (words == 4)
+        k_pack_sketch_rows<4><<<blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
+                                                            c->keysB[0].as<uint32_t>(), c->valsB[0].as<int32_t>(), or_key);
+    else
+        k_pack_sketch_rows<8><<<blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
+                                                            c->keysB[0].as<uint32_t>(), c->valsB[0].as<int32_t>(), or_key);
+    CKLC(c);
     return BF_OK;
 }
 
@@ -181,7 +219,7 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
     if (c->engine == BF_ENGINE_SKETCH) {
         int log2m = 0;
         while ((1 << log2m) < c->sketch_bits) ++log2m;
-        if (c->sketch_bits == 128 || c->sketch_bits == 256) {
+        if (staged_pack(c)) {   // step 2: staged sketches -> sorted tile layouts
             for (int f = 0; f < 2; ++f) TRY(folds[f].ensure((size_t)tiles * TILE * sizeof(uint32_t)));
             uint32_t* f8a = nullptr;   // expanded row operand (fragment order) and column operand (row-major)
             uint4* f8b = nullptr;
@@ -191,11 +229,10 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
                 f8b = fold8[1].as<uint4>();
             }
             uint32_t *b32 = bits.as<uint32_t>(), *fo0 = folds[0].as<uint32_t>(), *fo1 = folds[1].as<uint32_t>();
-            if (c->sketch_bits == 128) {
-                k_pack_sketch_reg<4><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, b32, fo0, fo1, f8a, f8b);
-            } else {
-                k_pack_sketch_reg<8><<<(unsigned)tiles, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m, b32, fo0, fo1, f8a, f8b);
-            }
+            if (c->sketch_bits == 128)
+                k_permute_store<4><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b);
+            else
+                k_permute_store<8><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b);
         } else {
             const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
             k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
@@ -228,7 +265,7 @@ int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t 
     const unsigned grid = (unsigned)(c->num_sms * bps);
     k_pairs<K4, STAGES, TWO_LEVEL><<<grid, PAIR_THREADS, L::kTotalBytes, c->stream>>>(
         A, B, c->n_chunks, nA, nB, c->items.as<int2>(), c->items_cap_used, c->wprefix.as<unsigned long long>(),
-        c->jlo.as<int32_t>(), c->tilesA, c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank,
+        c->jlo.as<int32_t>(), c->sched_entries, c->sched_ranges, c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank,
         c->world, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
@@ -391,7 +428,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
                       &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->sort_max, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->sk_rows, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -608,9 +645,21 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     DevBuf* keysA = c->has_query ? c->keysA : c->keysB;
     DevBuf* valsA = c->has_query ? c->valsA : c->valsB;
     if (active) {
-        // ---- K2: sort by cardinality
-        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0));
-        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1));
+        // ---- K2: sort keys (+ the staged sketches, which come out of the same pass over the columns) and sort
+        TRY(ensure_sort_buffers(c, nB, c->keysB, c->valsB));
+        if (c->has_query) TRY(ensure_sort_buffers(c, nA, c->keysA, c->valsA));
+        const bool staged = staged_pack(c);
+        if (staged) {
+            TRY(pack_stage_all_rows(c));
+            if (c->has_query) {   // before the sort of the B side reuses keysB[0]
+                k_gather_keys<<<grid_for(nA, 256), 256, 0, c->stream>>>(c->keysB[0].as<uint32_t>(), c->query_rows.as<int32_t>(), nA,
+                                                                        c->keysA[0].as<uint32_t>(), c->valsA[0].as<int32_t>(),
+                                                                        c->sort_max.as<uint32_t>() + 1);
+                CKLC(c);
+            }
+        }
+        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0, staged));
+        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1, staged));
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
     if (active) {
@@ -621,17 +670,21 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(c->ev[2], c->stream));
     if (active) {
         // ---- K2b: schedule
-        TRY(c->jlo.ensure((size_t)c->tilesA * sizeof(int32_t)));
-        TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
-        TRY(c->jend.ensure((size_t)c->tilesA * sizeof(int32_t)));
+        const int n_ranges = 2 * max_dist + 1;
+        const int64_t n_entries = c->tilesA * n_ranges;
+        c->sched_entries = n_entries;
+        c->sched_ranges = n_ranges;
+        TRY(c->jlo.ensure((size_t)n_entries * sizeof(int32_t)));
+        TRY(c->wprefix.ensure((size_t)(n_entries + 1) * sizeof(unsigned long long)));
+        TRY(c->jend.ensure((size_t)n_entries * sizeof(int32_t)));
         const int group = c->ran_two_kernel ? L1_GROUP : 1;
         k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
             keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1, group,
             c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),
             &c->counters.as<DevCounters>()->n_tilepairs);
         CKLC(c);
-        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
-        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
+        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + n_entries, 0, sizeof(unsigned long long), c->stream));
+        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), n_entries + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
         CKLC(c);
         DevCounters* dc = c->counters.as<DevCounters>();
         k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
@@ -650,7 +703,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             TRY(c->items.ensure((size_t)icap * sizeof(int2)));
             c->items_cap_used = icap;
             k_expand_items<<<c->num_sms * 8, 256, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(),
-                                                                  c->tilesA, c->nwork.as<unsigned long long>(), icap,
+                                                                  n_entries, n_ranges, c->nwork.as<unsigned long long>(), icap,
                                                                   c->items.as<int2>(), group, c->jend.as<int32_t>());
             CKLC(c);
         }

@@ -46,23 +46,50 @@ struct DevCounters {
 };
 
 // ------------------------------------------------------------------------------------------
-// K2: cardinality keys + stable LSD radix sort (2 x 8 bits) — deterministic permutation
+// K2: sort keys + stable LSD radix sort (up to 4 x 8 bits) — deterministic permutation
+//
+// key = c << 16 | s with c = |A| (the row's cardinality) and s = |A n H|, H = the columns whose hash has its top
+// bit set (s = 0 for the engines that do not stream the columns before the sort: H = {} is as valid as any H).
+// For two rows, |A xor B| >= |s_A - s_B| + |(c_A - s_A) - (c_B - s_B)|: the two halves of the column space are
+// disjoint.  Sorting by (c, s) therefore turns the partners of a row into at most 2 d + 1 contiguous runs, one
+// per c' = c - d .. c + d, each bounded in s (see k_schedule) - about five times fewer tile pairs than the plain
+// cardinality band on SARS-CoV-2-shaped profiles.  Both halves are clamped to 16 bits; k_schedule drops the s
+// bound wherever a clamped value could be involved, so the band test stays sound for any input.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sort_key(int64_t card, uint32_t sub) {
+    if (card >= (int64_t)KEY_CLAMP) return KEY_CLAMP << 16;   // clamped group: s carries no information
+    return ((uint32_t)card << 16) | sub;                      // sub <= card < 65535
+}
+
 __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
                             int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
-                            uint32_t* __restrict__ max_key) {
+                            uint32_t* __restrict__ or_key) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     uint32_t k = 0;
     if (q < n) {
         int32_t r = rows ? rows[q] : (int32_t)q;
-        int64_t c = indptr[r + 1] - indptr[r];
-        k = c > (int64_t)KEY_CLAMP ? KEY_CLAMP : (uint32_t)c;
+        k = sort_key(indptr[r + 1] - indptr[r], 0u);
         keys[q] = k;
         vals[q] = r;
     }
-    // warp max -> one atomic per warp; a radix pass whose digits are all zero is skipped
-    k = __reduce_max_sync(0xffffffffu, k);
-    if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(max_key, k);
+    // OR of all keys -> one atomic per warp; a radix pass whose digits are all zero is skipped
+    k = __reduce_or_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && k) atomicOr(or_key, k);
+}
+
+// keys of a row subset from the per-row keys of the whole matrix (written by k_pack_sketch_rows)
+__global__ void k_gather_keys(const uint32_t* __restrict__ row_keys, const int32_t* __restrict__ rows, int64_t n,
+                              uint32_t* __restrict__ keys, int32_t* __restrict__ vals, uint32_t* __restrict__ or_key) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    uint32_t k = 0;
+    if (q < n) {
+        const int32_t r = rows[q];
+        k = row_keys[r];
+        keys[q] = k;
+        vals[q] = r;
+    }
+    k = __reduce_or_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && k) atomicOr(or_key, k);
 }
 
 // One radix pass = k_sort_hist -> k_sort_scan_digits -> k_sort_scatter.  A block owns SORT_ITEMS
@@ -87,8 +114,8 @@ __device__ __forceinline__ void sort_warp_count(const uint32_t* __restrict__ key
 
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
                                                    uint32_t* __restrict__ counts, int nblocks,
-                                                   const uint32_t* __restrict__ max_key) {
-    if ((*max_key >> shift) == 0) return;  // every digit of this pass is 0: identity pass
+                                                   const uint32_t* __restrict__ or_key) {
+    if (((*or_key >> shift) & 255u) == 0) return;  // every digit of this pass is 0: identity pass
     __shared__ uint32_t whist[SORT_WARPS][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
@@ -106,8 +133,8 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ 
 // scan over the 256 digit totals itself.
 __global__ void __launch_bounds__(256) k_sort_scan_digits(uint32_t* __restrict__ counts, int nblocks,
                                                           uint32_t* __restrict__ totals, int shift,
-                                                          const uint32_t* __restrict__ max_key) {
-    if ((*max_key >> shift) == 0) return;
+                                                          const uint32_t* __restrict__ or_key) {
+    if (((*or_key >> shift) & 255u) == 0) return;
     const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint32_t* row = counts + (size_t)d * nblocks;
     uint32_t carry = 0;
@@ -132,9 +159,9 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ totals, int nblocks,
                                                       uint32_t* __restrict__ keys_out,
                                                       int32_t* __restrict__ vals_out,
-                                                      const uint32_t* __restrict__ max_key) {
+                                                      const uint32_t* __restrict__ or_key) {
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
-    if ((*max_key >> shift) == 0) {  // identity pass: plain copy
+    if (((*or_key >> shift) & 255u) == 0) {  // identity pass: plain copy
         const int m = (int)min((int64_t)SORT_ITEMS, n - base);
         for (int i = threadIdx.x; i < m; i += 256) {
             keys_out[base + i] = keys[base + i];
@@ -250,11 +277,19 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, i
 }
 
 // ------------------------------------------------------------------------------------------
-// K2b: band-pruned tile schedule.  keys are sorted ascending, so tile min/max are its ends and the
-// B tiles that can hold an in-band partner of A tile I form one contiguous range [jlo, jlo+count).
+// K2b: band-pruned tile schedule.  keys are sorted ascending, so a tile's min/max are its ends.
+// Row tile I gets n_ranges = 2 d + 1 schedule entries e = I * n_ranges + r, each one contiguous range
+// [jlo[e], jend[e]) of B tiles:
+//   * all rows of the tile share one (unclamped) cardinality c: entry r covers the partners of cardinality
+//     c' = c - d + r.  With D = c' - c, a partner needs |s' - s| + |D - (s' - s)| <= d, i.e.
+//     s' - s in [-(d - D) / 2, (D + d) / 2] (integer divisions of non-negative numbers), so the entry is the run
+//     c' << 16 | smin - (d - D) / 2  ..  c' << 16 | smax + (D + d) / 2; no s bound against the clamped group;
+//   * otherwise (tile across a cardinality boundary, or clamped rows): entry 0 = the plain cardinality band
+//     cmin - d .. cmax + d, the other entries empty.
+// Ranges are clipped so that no B tile is listed twice for a row tile (and to J >= I in the triangular case).
 // ------------------------------------------------------------------------------------------
 // `group` column tiles form one work item (1 for the single-kernel path, L1_GROUP for the two-kernel
-// path); count[I] = number of work items of row tile I, *n_tilepairs += number of tile pairs.
+// path); count[e] = number of work items of entry e, *n_tilepairs += number of tile pairs.
 __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const uint32_t* __restrict__ keysB,
                            int64_t nB, int max_dist, int triangular, int group, int32_t* __restrict__ jlo,
                            int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
@@ -262,44 +297,72 @@ __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const
     const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
     int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (I >= tA) return;
-    const uint32_t aMin = keysA[I * TILE];
-    const uint32_t aMax = keysA[min(nA, (I + 1) * TILE) - 1];
-    const uint32_t lo_t = aMin > (uint32_t)max_dist ? aMin - (uint32_t)max_dist : 0u;
-    const uint32_t hi_t = aMax + (uint32_t)max_dist;
-    // first J with bMax[J] >= lo_t
-    int64_t l = 0, r = tB;
-    while (l < r) {
-        int64_t mid = (l + r) >> 1;
-        uint32_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
-        if (bMax >= lo_t) r = mid; else l = mid + 1;
+    const int n_ranges = 2 * max_dist + 1;
+    const uint32_t kMin = keysA[I * TILE], kMax = keysA[min(nA, (I + 1) * TILE) - 1];
+    const int64_t cMin = kMin >> 16, cMax = kMax >> 16, sMin = kMin & 0xffffu, sMax = kMax & 0xffffu;
+    const bool single = cMin == cMax && cMax < (int64_t)KEY_CLAMP;
+    int64_t prev_end = triangular ? I : 0;
+    unsigned long long tp_sum = 0;
+    for (int r = 0; r < n_ranges; ++r) {
+        int64_t lo_key = 1, hi_key = 0;   // empty
+        if (single) {
+            const int64_t D = (int64_t)r - max_dist, c2 = cMin + D;
+            if (c2 >= 0 && c2 <= (int64_t)KEY_CLAMP) {
+                int64_t s_lo = 0, s_hi = 0xffff;
+                if (c2 < (int64_t)KEY_CLAMP) {
+                    s_lo = max((int64_t)0, sMin - (max_dist - D) / 2);
+                    s_hi = min((int64_t)0xffff, sMax + (D + max_dist) / 2);
+                }
+                lo_key = (c2 << 16) | s_lo;
+                hi_key = (c2 << 16) | s_hi;
+            }
+        } else if (r == 0) {
+            lo_key = max((int64_t)0, cMin - max_dist) << 16;
+            hi_key = (min((int64_t)KEY_CLAMP, cMax + max_dist) << 16) | 0xffff;
+        }
+        int64_t first = prev_end, end = prev_end;
+        if (lo_key <= hi_key) {
+            // first J with bMax[J] >= lo_key
+            int64_t l = 0, rr = tB;
+            while (l < rr) {
+                const int64_t mid = (l + rr) >> 1;
+                const uint32_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
+                if ((int64_t)bMax >= lo_key) rr = mid; else l = mid + 1;
+            }
+            first = l;
+            // first J with bMin[J] > hi_key
+            l = 0; rr = tB;
+            while (l < rr) {
+                const int64_t mid = (l + rr) >> 1;
+                const uint32_t bMin = keysB[mid * TILE];
+                if ((int64_t)bMin > hi_key) rr = mid; else l = mid + 1;
+            }
+            end = l;
+            first = max(first, prev_end);
+            end = max(end, first);
+            prev_end = end;
+        }
+        const int64_t e = I * n_ranges + r;
+        jlo[e] = (int32_t)first;
+        jend[e] = (int32_t)end;
+        const unsigned long long tp = (unsigned long long)(end - first);
+        count[e] = (tp + group - 1) / group;
+        tp_sum += tp;
     }
-    int64_t first = l;
-    // first J with bMin[J] > hi_t
-    l = 0; r = tB;
-    while (l < r) {
-        int64_t mid = (l + r) >> 1;
-        uint32_t bMin = keysB[mid * TILE];
-        if (bMin > hi_t) r = mid; else l = mid + 1;
-    }
-    int64_t end = l;
-    if (triangular && first < I) first = I;
-    jlo[I] = (int32_t)first;
-    jend[I] = (int32_t)max(end, first);
-    const unsigned long long tp = end > first ? (unsigned long long)(end - first) : 0ull;
-    count[I] = (tp + group - 1) / group;
-    if (tp) atomicAdd(n_tilepairs, tp);
+    if (tp_sum) atomicAdd(n_tilepairs, tp_sum);
 }
 
-// ordered in-band count: for every x in X, #{y in Y : |key_x - key_y| <= d}
+// ordered in-band count: for every x in X, #{y in Y : ||x| - |y|| <= d}
 __global__ void __launch_bounds__(256) k_band_count(const uint32_t* __restrict__ keysX, int64_t nX,
                                                     const uint32_t* __restrict__ keysY, int64_t nY, int max_dist,
                                                     unsigned long long* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned long long c = 0;
     if (i < nX) {
-        uint32_t k = keysX[i];
-        uint32_t lo_t = k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u;
-        uint32_t hi_t = k + (uint32_t)max_dist;
+        // the metric's candidate pairs are defined on the cardinalities alone (upper key halves)
+        const uint32_t k = keysX[i] >> 16;
+        const uint32_t lo_t = (k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u) << 16;
+        const uint32_t hi_t = (min(k + (uint32_t)max_dist, KEY_CLAMP) << 16) | 0xffffu;
         int64_t l = 0, r = nY;
         while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] >= lo_t) r = m; else l = m + 1; }
         int64_t a = l;
@@ -430,43 +493,43 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
     }
 }
 
-// SKETCH, m = 32*WORDS <= 256 bits.  A block builds one sorted tile (128 rows).  Rows are short (about 90 columns),
-// so a warp folds FOUR rows at a time, eight lanes each: every lane XORs the bits of its columns straight into the
-// row's sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction), four loads per
-// lane in flight.  Afterwards thread t stores row t: all 128 rows of the tile at once, coalesced.
-// Reads 4*nnz + 12*N bytes, writes N*(m/8 + 8 [+ 64]) bytes.
+// SKETCH, m = 32*WORDS <= 256 bits, step 1 of 2 (before the sort): one pass over the CSR in storage order gives
+// every row its sketch (row-major staging, 4*WORDS bytes per row) AND its sort key c << 16 | s (see K2).
+// A block takes 128 consecutive rows - one contiguous stretch of `indices`.  Rows are short (about 90 columns), so a
+// warp folds FOUR rows at a time, eight lanes each: every lane XORs the bits of its columns straight into the row's
+// sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction; one ATOMS.ADD more
+// for the columns of H), four loads per lane in flight.  Reads 4*nnz + 8*N bytes, writes N*(m/8 + 8) bytes.
 // (Measured alternatives at 1 M rows of ~89 columns: a warp per row with per-lane word selects + redux.sync and
-// lane-0 stores: 0.34 ms; the same reading the CSR in storage order and scattering the outputs: 0.34 ms - the
-// gather is not the limit; a thread per row: 0.69 ms, its 32-sector loads are L1-wavefront bound; this: 0.13 ms.)
+// lane-0 stores: 0.34 ms, in sorted (gather) or storage order alike; a thread per row: 0.69 ms, its 32-sector
+// loads are L1-wavefront bound; the shared-memory form: 0.13 ms.)
 template <int WORDS>
-__global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restrict__ indptr,
-                                                         const int32_t* __restrict__ indices,
-                                                         const int32_t* __restrict__ perm, int64_t n, int log2m,
-                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
-                                                         uint32_t* __restrict__ foldB, uint32_t* __restrict__ fold8a,
-                                                         uint4* __restrict__ fold8b) {
+__global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ indices, int64_t n, int log2m,
+                                                          uint32_t* __restrict__ sk_rows, uint32_t* __restrict__ keys,
+                                                          int32_t* __restrict__ vals, uint32_t* __restrict__ or_key) {
     __shared__ uint32_t sk[TILE][WORDS];
+    __shared__ uint32_t sub[TILE];
     __shared__ int64_t row_b[TILE], row_e[TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = blockIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * TILE;
     if (threadIdx.x < TILE) {
-        const int64_t p = tile * TILE + threadIdx.x;
-        int64_t b = 0, e = 0;   // rows past n stay all-zero (never emitted: index check in the pair kernels)
-        if (p < n) {
-            const int32_t r = perm[p];
+        const int64_t r = row0 + threadIdx.x;
+        int64_t b = 0, e = 0;
+        if (r < n) {
             b = indptr[r];
             e = indptr[r + 1];
         }
         row_b[threadIdx.x] = b;
         row_e[threadIdx.x] = e;
+        sub[threadIdx.x] = 0u;
 #pragma unroll
         for (int t = 0; t < WORDS; ++t) sk[threadIdx.x][t] = 0u;
     }
     __syncthreads();
-    const int sub = lane >> 3, l8 = lane & 7;
+    const int sg = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
     for (int k = 0; k < TILE / 32; ++k) {
-        const int row = warp * (TILE / 8) + 4 * k + sub;
+        const int row = warp * (TILE / 8) + 4 * k + sg;
         const int64_t e = row_e[row];
         uint32_t* dst = sk[row];
         for (int64_t q = row_b[row] + l8; q < e; q += 32) {
@@ -478,17 +541,49 @@ __global__ void __launch_bounds__(256) k_pack_sketch_reg(const int64_t* __restri
                 if (col[t] >= 0) {   // column ids are non-negative
                     const uint32_t h = fold_hash((uint32_t)col[t], log2m);
                     atomicXor(&dst[h >> 5], 1u << (h & 31));
+                    if (h >> (log2m - 1)) atomicAdd(&sub[row], 1u);   // H = columns with the top hash bit set
                 }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x < TILE) {
-        uint32_t w[WORDS];
+    uint32_t key = 0;
+    if (threadIdx.x < TILE && row0 + threadIdx.x < n) {
+        const int64_t r = row0 + threadIdx.x;
+        uint32_t* out = sk_rows + (size_t)r * WORDS;
 #pragma unroll
-        for (int t = 0; t < WORDS; ++t) w[t] = sk[threadIdx.x][t];
-        pack_store_row<WORDS>(w, tile, threadIdx.x, bits, foldA, foldB, fold8a, fold8b);
+        for (int g = 0; g < WORDS / 4; ++g)
+            reinterpret_cast<uint4*>(out)[g] = make_uint4(sk[threadIdx.x][4 * g], sk[threadIdx.x][4 * g + 1],
+                                                          sk[threadIdx.x][4 * g + 2], sk[threadIdx.x][4 * g + 3]);
+        key = sort_key(row_e[threadIdx.x] - row_b[threadIdx.x], sub[threadIdx.x]);
+        keys[r] = key;
+        vals[r] = (int32_t)r;
     }
+    key = __reduce_or_sync(0xffffffffu, key);
+    if (lane == 0 && key) atomicOr(or_key, key);
+}
+
+// step 2 of 2 (after the sort): thread p of block `tile` fetches the staged sketch of the row at sorted position
+// tile * 128 + p and writes all derived layouts of that slot (pack_store_row); pad slots are zero-filled.
+template <int WORDS>
+__global__ void __launch_bounds__(TILE) k_permute_store(const uint32_t* __restrict__ sk_rows,
+                                                        const int32_t* __restrict__ perm, int64_t n,
+                                                        uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
+                                                        uint32_t* __restrict__ foldB, uint32_t* __restrict__ fold8a,
+                                                        uint4* __restrict__ fold8b) {
+    const int64_t p = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    uint32_t w[WORDS];
+#pragma unroll
+    for (int t = 0; t < WORDS; ++t) w[t] = 0u;   // rows past n stay all-zero (never emitted: index check in the pair kernels)
+    if (p < n) {
+        const uint4* src = reinterpret_cast<const uint4*>(sk_rows + (size_t)perm[p] * WORDS);
+#pragma unroll
+        for (int g = 0; g < WORDS / 4; ++g) {
+            const uint4 v = __ldg(&src[g]);
+            w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
+        }
+    }
+    pack_store_row<WORDS>(w, blockIdx.x, threadIdx.x, bits, foldA, foldB, fold8a, fold8b);
 }
 
 // FULL: bit matrix pre-zeroed by the host (cudaMemsetAsync); one warp per row sets its bits.
@@ -552,24 +647,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // ------------------------------------------------------------------------------------------
 // With group > 1 an item covers column tiles J0 .. J0+cnt-1 (cnt <= group <= 4) and is stored as
 // (I, J0 | (cnt-1) << 29); jcount[I] (tile pairs of row tile I) is recomputed from the next prefix.
+// n_entries = row tiles * n_ranges schedule entries (entry e belongs to row tile e / n_ranges)
 __global__ void k_expand_items(const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo,
-                               int64_t tilesA, const unsigned long long* __restrict__ n_work,
+                               int64_t n_entries, int n_ranges, const unsigned long long* __restrict__ n_work,
                                unsigned long long cap, int2* __restrict__ items, int group,
                                const int32_t* __restrict__ jend) {
     const unsigned long long W = min(*n_work, cap);
     for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < W;
          w += (unsigned long long)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = tilesA - 1;  // largest I with wprefix[I] <= w
+        int64_t lo = 0, hi = n_entries - 1;  // largest e with wprefix[e] <= w (never an empty entry)
         while (lo < hi) {
             const int64_t mid = (lo + hi + 1) >> 1;
             if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
         }
+        const int I = (int)(lo / n_ranges);
         if (group == 1) {
-            items[w] = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+            items[w] = make_int2(I, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
         } else {
             const int j0 = __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])) * group;
             const int cnt = min(group, __ldg(&jend[lo]) - j0);
-            items[w] = make_int2((int)lo, j0 | ((cnt - 1) << 29));
+            items[w] = make_int2(I, j0 | ((cnt - 1) << 29));
         }
     }
 }
@@ -602,7 +699,7 @@ template <int K4, int STAGES, bool TWO_LEVEL>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_chunks, int64_t nA, int64_t nB,
         const int2* __restrict__ items, unsigned long long items_cap,
-        const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo, int64_t tilesA,
+        const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo, int64_t n_entries, int n_ranges,
         const unsigned long long* __restrict__ n_work, int threshold, int triangular, int rank, int world,
         uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
     using L = PairSmem<K4, STAGES>;
@@ -636,12 +733,12 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
                 if (w < items_cap) {
                     mine = __ldg(&items[w]);
                 } else {  // beyond the expanded table (huge bands): map w -> (I, J) by binary search
-                    int64_t lo = 0, hi = tilesA - 1;
+                    int64_t lo = 0, hi = n_entries - 1;   // schedule entry; its row tile is lo / n_ranges
                     while (lo < hi) {
                         const int64_t mid = (lo + hi + 1) >> 1;
                         if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
                     }
-                    mine = make_int2((int)lo, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+                    mine = make_int2((int)(lo / n_ranges), __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
                 }
             }
             for (int l = 0; l < 32; ++l) {
