@@ -107,8 +107,7 @@ struct bf_ctx {
     int K4 = 1, n_chunks = 1;
     int64_t bits_per_row = 0, tilesA = 0, tilesB = 0;
     unsigned long long cand_cap_used = 0, items_cap_used = 0;
-    int64_t sched_entries = 0;   // schedule entries of the last run = row tiles * sched_ranges
-    int sched_ranges = 1;
+    int sched_ranges = 1;   // schedule entries per row tile of the last run (2 max_dist + 1)
     bool ran_two_level = false, ran_two_kernel = false;
     unsigned long long queue_cap_used = 0;
     float ms_h2d = 0, ms_merge = 0, ms_d2h = 0;
@@ -265,7 +264,7 @@ int launch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t 
     const unsigned grid = (unsigned)(c->num_sms * bps);
     k_pairs<K4, STAGES, TWO_LEVEL><<<grid, PAIR_THREADS, L::kTotalBytes, c->stream>>>(
         A, B, c->n_chunks, nA, nB, c->items.as<int2>(), c->items_cap_used, c->wprefix.as<unsigned long long>(),
-        c->jlo.as<int32_t>(), c->sched_entries, c->sched_ranges, c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank,
+        c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->tilesA, c->sched_ranges, c->nwork.as<unsigned long long>(), c->max_dist, triangular, c->rank,
         c->world, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
@@ -672,10 +671,9 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         // ---- K2b: schedule
         const int n_ranges = 2 * max_dist + 1;
         const int64_t n_entries = c->tilesA * n_ranges;
-        c->sched_entries = n_entries;
         c->sched_ranges = n_ranges;
         TRY(c->jlo.ensure((size_t)n_entries * sizeof(int32_t)));
-        TRY(c->wprefix.ensure((size_t)(n_entries + 1) * sizeof(unsigned long long)));
+        TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
         TRY(c->jend.ensure((size_t)n_entries * sizeof(int32_t)));
         const int group = c->ran_two_kernel ? L1_GROUP : 1;
         k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
@@ -683,8 +681,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),
             &c->counters.as<DevCounters>()->n_tilepairs);
         CKLC(c);
-        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + n_entries, 0, sizeof(unsigned long long), c->stream));
-        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), n_entries + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
+        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
+        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
         CKLC(c);
         DevCounters* dc = c->counters.as<DevCounters>();
         k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
@@ -703,7 +701,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
             TRY(c->items.ensure((size_t)icap * sizeof(int2)));
             c->items_cap_used = icap;
             k_expand_items<<<c->num_sms * 8, 256, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->jlo.as<int32_t>(),
-                                                                  n_entries, n_ranges, c->nwork.as<unsigned long long>(), icap,
+                                                                  c->tilesA, n_ranges, c->nwork.as<unsigned long long>(), icap,
                                                                   c->items.as<int2>(), group, c->jend.as<int32_t>());
             CKLC(c);
         }

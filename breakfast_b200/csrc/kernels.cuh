@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, i
 // Ranges are clipped so that no B tile is listed twice for a row tile (and to J >= I in the triangular case).
 // ------------------------------------------------------------------------------------------
 // `group` column tiles form one work item (1 for the single-kernel path, L1_GROUP for the two-kernel
-// path); count[e] = number of work items of entry e, *n_tilepairs += number of tile pairs.
+// path); an item never spans two entries; count[I] = number of work items of row tile I (all its entries),
+// *n_tilepairs += number of tile pairs.
 __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const uint32_t* __restrict__ keysB,
                            int64_t nB, int max_dist, int triangular, int group, int32_t* __restrict__ jlo,
                            int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
@@ -302,7 +303,7 @@ __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const
     const int64_t cMin = kMin >> 16, cMax = kMax >> 16, sMin = kMin & 0xffffu, sMax = kMax & 0xffffu;
     const bool single = cMin == cMax && cMax < (int64_t)KEY_CLAMP;
     int64_t prev_end = triangular ? I : 0;
-    unsigned long long tp_sum = 0;
+    unsigned long long tp_sum = 0, items_sum = 0;
     for (int r = 0; r < n_ranges; ++r) {
         int64_t lo_key = 1, hi_key = 0;   // empty
         if (single) {
@@ -346,29 +347,37 @@ __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const
         jlo[e] = (int32_t)first;
         jend[e] = (int32_t)end;
         const unsigned long long tp = (unsigned long long)(end - first);
-        count[e] = (tp + group - 1) / group;
+        items_sum += (tp + group - 1) / group;
         tp_sum += tp;
     }
+    count[I] = items_sum;
     if (tp_sum) atomicAdd(n_tilepairs, tp_sum);
 }
 
-// ordered in-band count: for every x in X, #{y in Y : ||x| - |y|| <= d}
+// ordered in-band count: for every x in X, #{y in Y : ||x| - |y|| <= d}.  The metric's candidate pairs are defined
+// on the cardinalities alone (upper key halves).  X is sorted, so only the first row of every run of equal
+// cardinality searches (three binary searches) and counts for its whole run.
 __global__ void __launch_bounds__(256) k_band_count(const uint32_t* __restrict__ keysX, int64_t nX,
                                                     const uint32_t* __restrict__ keysY, int64_t nY, int max_dist,
                                                     unsigned long long* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned long long c = 0;
     if (i < nX) {
-        // the metric's candidate pairs are defined on the cardinalities alone (upper key halves)
         const uint32_t k = keysX[i] >> 16;
-        const uint32_t lo_t = (k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u) << 16;
-        const uint32_t hi_t = (min(k + (uint32_t)max_dist, KEY_CLAMP) << 16) | 0xffffu;
-        int64_t l = 0, r = nY;
-        while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] >= lo_t) r = m; else l = m + 1; }
-        int64_t a = l;
-        l = a; r = nY;
-        while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] > hi_t) r = m; else l = m + 1; }
-        c = (unsigned long long)(l - a);
+        if (i == 0 || (keysX[i - 1] >> 16) != k) {
+            const uint32_t lo_t = (k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u) << 16;
+            const uint32_t hi_t = (min(k + (uint32_t)max_dist, KEY_CLAMP) << 16) | 0xffffu;
+            const uint32_t run_t = (k << 16) | 0xffffu;
+            int64_t l = i, r = nX;   // end of this run in X
+            while (l < r) { int64_t m = (l + r) >> 1; if (keysX[m] > run_t) r = m; else l = m + 1; }
+            const int64_t run = l - i;
+            l = 0; r = nY;
+            while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] >= lo_t) r = m; else l = m + 1; }
+            const int64_t a = l;
+            r = nY;
+            while (l < r) { int64_t m = (l + r) >> 1; if (keysY[m] > hi_t) r = m; else l = m + 1; }
+            c = (unsigned long long)run * (unsigned long long)(l - a);
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -532,6 +541,7 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         const int row = warp * (TILE / 8) + 4 * k + sg;
         const int64_t e = row_e[row];
         uint32_t* dst = sk[row];
+        uint32_t in_h = 0;   // this lane's columns in H = those with the top hash bit set
         for (int64_t q = row_b[row] + l8; q < e; q += 32) {
             int32_t col[4];
 #pragma unroll
@@ -541,10 +551,11 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
                 if (col[t] >= 0) {   // column ids are non-negative
                     const uint32_t h = fold_hash((uint32_t)col[t], log2m);
                     atomicXor(&dst[h >> 5], 1u << (h & 31));
-                    if (h >> (log2m - 1)) atomicAdd(&sub[row], 1u);   // H = columns with the top hash bit set
+                    in_h += h >> (log2m - 1);
                 }
             }
         }
+        if (in_h) atomicAdd(&sub[row], in_h);
     }
     __syncthreads();
     uint32_t key = 0;
@@ -647,27 +658,38 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // ------------------------------------------------------------------------------------------
 // With group > 1 an item covers column tiles J0 .. J0+cnt-1 (cnt <= group <= 4) and is stored as
 // (I, J0 | (cnt-1) << 29); jcount[I] (tile pairs of row tile I) is recomputed from the next prefix.
-// n_entries = row tiles * n_ranges schedule entries (entry e belongs to row tile e / n_ranges)
+// work item w of row tile I (wprefix[I] <= w < wprefix[I + 1]) -> (first column tile, number of column tiles):
+// walk the tile's n_ranges schedule entries
+__device__ __forceinline__ int2 item_of_tile(int64_t I, unsigned long long off, int n_ranges, int group,
+                                             const int32_t* __restrict__ jlo, const int32_t* __restrict__ jend) {
+    int j0 = 0, cnt = 1;
+    for (int r = 0; r < n_ranges; ++r) {
+        const int lo = __ldg(&jlo[I * n_ranges + r]), en = __ldg(&jend[I * n_ranges + r]);
+        const unsigned long long n_r = (unsigned long long)(en - lo + group - 1) / group;
+        if (off < n_r) {
+            j0 = lo + (int)off * group;
+            cnt = min(group, en - j0);
+            break;
+        }
+        off -= n_r;
+    }
+    return make_int2(j0, cnt);
+}
+
 __global__ void k_expand_items(const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo,
-                               int64_t n_entries, int n_ranges, const unsigned long long* __restrict__ n_work,
+                               int64_t tilesA, int n_ranges, const unsigned long long* __restrict__ n_work,
                                unsigned long long cap, int2* __restrict__ items, int group,
                                const int32_t* __restrict__ jend) {
     const unsigned long long W = min(*n_work, cap);
     for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < W;
          w += (unsigned long long)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = n_entries - 1;  // largest e with wprefix[e] <= w (never an empty entry)
+        int64_t lo = 0, hi = tilesA - 1;  // largest I with wprefix[I] <= w (never a tile without items)
         while (lo < hi) {
             const int64_t mid = (lo + hi + 1) >> 1;
             if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
         }
-        const int I = (int)(lo / n_ranges);
-        if (group == 1) {
-            items[w] = make_int2(I, __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
-        } else {
-            const int j0 = __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])) * group;
-            const int cnt = min(group, __ldg(&jend[lo]) - j0);
-            items[w] = make_int2(I, j0 | ((cnt - 1) << 29));
-        }
+        const int2 jc = item_of_tile(lo, w - __ldg(&wprefix[lo]), n_ranges, group, jlo, jend);
+        items[w] = make_int2((int)lo, group == 1 ? jc.x : (jc.x | ((jc.y - 1) << 29)));
     }
 }
 
@@ -699,7 +721,8 @@ template <int K4, int STAGES, bool TWO_LEVEL>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_chunks, int64_t nA, int64_t nB,
         const int2* __restrict__ items, unsigned long long items_cap,
-        const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo, int64_t n_entries, int n_ranges,
+        const unsigned long long* __restrict__ wprefix, const int32_t* __restrict__ jlo,
+        const int32_t* __restrict__ jend, int64_t tilesA, int n_ranges,
         const unsigned long long* __restrict__ n_work, int threshold, int triangular, int rank, int world,
         uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
     using L = PairSmem<K4, STAGES>;
@@ -733,12 +756,12 @@ k_pairs(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int n_
                 if (w < items_cap) {
                     mine = __ldg(&items[w]);
                 } else {  // beyond the expanded table (huge bands): map w -> (I, J) by binary search
-                    int64_t lo = 0, hi = n_entries - 1;   // schedule entry; its row tile is lo / n_ranges
+                    int64_t lo = 0, hi = tilesA - 1;
                     while (lo < hi) {
                         const int64_t mid = (lo + hi + 1) >> 1;
                         if (__ldg(&wprefix[mid]) <= w) lo = mid; else hi = mid - 1;
                     }
-                    mine = make_int2((int)(lo / n_ranges), __ldg(&jlo[lo]) + (int)(w - __ldg(&wprefix[lo])));
+                    mine = make_int2((int)lo, item_of_tile(lo, w - __ldg(&wprefix[lo]), n_ranges, 1, jlo, jend).x);
                 }
             }
             for (int l = 0; l < 32; ++l) {
@@ -1007,7 +1030,8 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
 // (accumulator round-trip latency with K = 32, see tools/experiments/l1_tcgen05_kernel.cuh.txt).
 // ------------------------------------------------------------------------------------------
 constexpr int IMMA_STAGES = 6;
-constexpr int L2_SUB = 8;       // CTAs of k_pairs_l2_pair per queue segment
+constexpr int L2_CBUF = 1024;   // candidates a CTA of k_pairs_l2_unit collects per round before one cursor update
+constexpr int L2_SUB = 64;      // CTAs of k_pairs_l2_unit per queue segment (one unit per thread for segments up to 16 K units)
 constexpr int IMMA_TILE_BYTES = TILE * 32;
 constexpr int IMMA_STAGE_BYTES = (1 + L1_GROUP) * IMMA_TILE_BYTES;
 constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
@@ -1155,8 +1179,17 @@ k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB
     const int sgm = blockIdx.x / L2_SUB, sub = blockIdx.x % L2_SUB;
     const unsigned n = min(__ldg(&seg_counts[sgm]), seg_cap);
     const int2* seg = queue + (size_t)sgm * seg_cap;
+    // candidates are collected per CTA and appended with ONE global cursor update per round: a contended
+    // same-address atomic per candidate (about one per nanosecond device-wide) was most of this kernel's time
+    __shared__ uint2 cbuf[L2_CBUF];
+    __shared__ unsigned cbuf_n, checks_n;
+    __shared__ unsigned long long cbuf_base;
+    if (threadIdx.x == 0) cbuf_n = checks_n = 0;
+    __syncthreads();
     unsigned full_checks = 0;
-    for (unsigned u = sub * blockDim.x + threadIdx.x; u < n; u += L2_SUB * blockDim.x) {
+    for (unsigned u0 = sub * blockDim.x; u0 < n; u0 += L2_SUB * blockDim.x) {   // uniform over the CTA
+      const unsigned u = u0 + threadIdx.x;
+      if (u < n) {
         const int2 unit = __ldg(&seg[u]);
         const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
         const int r0 = tx >> 2, c0 = 8 * ty + 2 * (tx & 3);
@@ -1192,13 +1225,29 @@ k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB
                 d += __popc(x.x ^ y.x) + __popc(x.y ^ y.y) + __popc(x.z ^ y.z) + __popc(x.w ^ y.w);
             }
             if (d <= threshold) {
-                const unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
-                if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
+                const unsigned slot = atomicAdd(&cbuf_n, 1u);
+                if (slot < L2_CBUF) {
+                    cbuf[slot] = make_uint2((uint32_t)gi, (uint32_t)gj);
+                } else {   // buffer full (a dense cluster): append directly
+                    const unsigned long long pos = atomicAdd(&counters->n_cand, 1ull);
+                    if (pos < cand_cap) cand[pos] = make_uint2((uint32_t)gi, (uint32_t)gj);
+                }
             }
         }
+      }
+      __syncthreads();
+      const unsigned m = min(cbuf_n, (unsigned)L2_CBUF);
+      if (threadIdx.x == 0 && m) cbuf_base = atomicAdd(&counters->n_cand, (unsigned long long)m);
+      __syncthreads();
+      for (unsigned i = threadIdx.x; i < m; i += blockDim.x)
+          if (cbuf_base + i < cand_cap) cand[cbuf_base + i] = cbuf[i];
+      __syncthreads();
+      if (threadIdx.x == 0) cbuf_n = 0;
+      __syncthreads();
     }
-    full_checks = __reduce_add_sync(0xffffffffu, full_checks);
-    if ((threadIdx.x & 31) == 0 && full_checks) atomicAdd(&counters->l2_warp_items, (unsigned long long)full_checks);
+    if (full_checks) atomicAdd(&checks_n, full_checks);
+    __syncthreads();
+    if (threadIdx.x == 0 && checks_n) atomicAdd(&counters->l2_warp_items, (unsigned long long)checks_n);
 }
 
 // UNIT_IMMA = false: unit = the 8 x 4 pairs (ty + 16 i, tx + 32 j) of a k_pairs_l1 thread
@@ -1391,7 +1440,9 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                         // Rows of up to 128 columns (nearly all): each lane loads its <= 4 columns of either row once
                         // (positions lane + 32 s; all eight loads independent and issued back to back, so a candidate
                         // costs about one memory round trip) and gets the +-DWIN neighbours of B from lane rotations
-                        // instead of more loads - the kernel is bound by issued instructions, not by bytes.
+                        // instead of more loads.  (Equalising the batches over the warps - 26 candidates in each of three
+                        // rounds instead of 32/32/0-or-32 at 1 M rows - was measured slower, 289 vs 238 us: the scattered
+                        // row reads run at about 2.4 TB/s and more warps in flight do not raise that.)
                         const int32_t* pa = indices + ia;
                         const int32_t* pb = indices + ib;
                         const int la32 = (int)la, lb32 = (int)lb;
