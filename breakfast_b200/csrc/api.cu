@@ -330,10 +330,10 @@ int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int
     CKLC(c);
     CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
     if (c->K4 == 1)
-        k_pairs_l2<1, false><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+        k_pairs_l2<1><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
                                                             tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     else
-        k_pairs_l2<2, false><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
+        k_pairs_l2<2><<<c->num_sms * 8, 256, 0, c->stream>>>(A, B, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->max_dist,
                                                             tri, c->cand.as<uint2>(), c->cand_cap_used, c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;

@@ -1,17 +1,22 @@
 // kernels.cuh — sm_100a device code for the breakfast distance-and-clustering hot path.
 //
-// Pipeline (one pass = bf_run):
-//   K2  k_card_keys + 2x(k_sort_hist, k_scan, k_sort_scatter)   rows sorted by cardinality
-//                                                               (replaces the np.isclose band, breakfast.py:250-254)
-//   K1  k_pack_sketch / k_pack_full                              CSR -> tile-blocked bitsets
+// Pipeline (one pass = bf_run), default form (128/256-bit sketches, tensor-core level 1):
+//   K1a k_pack_sketch_rows                                       CSR in storage order -> staged sketches + sort keys
 //                                                               (replaces csr_matrix + row sums, breakfast.py:214,287)
-//   K2b k_schedule + k_scan                                      band-pruned tile-pair work list
-//   K3  k_pairs<K4>                                              tiled XOR/POPC + threshold + compaction
-//                                                               (replaces sklearn _sparse_manhattan + _reduce_func,
+//   K2  4x(k_sort_hist, k_sort_scan_digits, k_sort_scatter)      rows sorted by (cardinality, cardinality on one hash half)
+//                                                               (replaces the np.isclose band, breakfast.py:250-254)
+//   K1b k_permute_store                                          staged sketches -> tile-blocked bitsets, fold planes,
+//                                                               +-1 int8 operands
+//   K2b k_schedule + k_exclusive_scan + k_expand_items           two-key band-pruned tile-pair work list
+//   K3a k_pairs_l1_imma                                          level 1: int8 mma.sync on the 32-bit folds, survivors queued
+//   K3b k_pairs_l2_unit                                          level 2: exact 32-bit test, full-width XOR/POPC, candidates
+//                                                               (K3a+K3b replace sklearn _sparse_manhattan + _reduce_func,
 //                                                                sklearn/metrics/_pairwise_fast.pyx:76-107, breakfast.py:226-228)
-//   K3b k_verify_unite                                           exact |A xor B| on CSR rows of the survivors + union
-//   K4  k_uf_* (hook / pointer-jump / labels)                    replaces _to_graph + networkx connected_components
+//   K3c k_verify_unite                                           exact |A xor B| on CSR rows of the candidates + union
+//   K4  k_uf_* (hook / path halving / labels)                    replaces _to_graph + networkx connected_components
 //                                                               (breakfast.py:93-113,325-326)
+// Other forms: k_card_keys + k_pack_sketch / k_pack_full (wider sketches, FULL engine), k_pairs<K4> (single-kernel
+// tiled XOR/POPC + threshold + compaction), k_pairs_l1 + k_pairs_l2 (level 1 on the integer pipes).
 //
 // Bitset layout in HBM ("tile-blocked"): rows are in cardinality-sorted order, grouped in tiles of
 // TILE=128 rows.  A row's bitset is cut into chunks of 4*K4 32-bit words (K4 = 16-byte groups per
@@ -1250,10 +1255,8 @@ k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB
     if (threadIdx.x == 0 && checks_n) atomicAdd(&counters->l2_warp_items, (unsigned long long)checks_n);
 }
 
-// UNIT_IMMA = false: unit = the 8 x 4 pairs (ty + 16 i, tx + 32 j) of a k_pairs_l1 thread
-// UNIT_IMMA = true : unit = the 16 x 2 pairs (16 (i/2) + tx/4 + 8 (i%2), 8 ty + 2 (tx%4) + j) of a k_pairs_l1_imma
-//                    thread (the accumulator fragment of 8 m16n8k32 MMAs), i < 16, j < 2
-template <int K4, bool UNIT_IMMA>
+// level 2 of the integer-pipe level 1: unit = the 8 x 4 pairs (ty + 16 i, tx + 32 j) of a k_pairs_l1 thread
+template <int K4>
 __global__ void __launch_bounds__(256)
 k_pairs_l2(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int64_t nA, int64_t nB,
            const int2* __restrict__ queue, unsigned long long queue_cap, int threshold, int triangular,
@@ -1267,9 +1270,9 @@ k_pairs_l2(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, int
         const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
         const uint4* gA = bitsA + (size_t)I * (K4 * TILE);
         const uint4* gB = bitsB + (size_t)J * (K4 * TILE);
-        constexpr int NI = UNIT_IMMA ? 16 : 8, NJ = UNIT_IMMA ? 2 : 4;
-        auto row_of = [&](int i) { return UNIT_IMMA ? 16 * (i >> 1) + (tx >> 2) + 8 * (i & 1) : ty + 16 * i; };
-        auto col_of = [&](int j) { return UNIT_IMMA ? 8 * ty + 2 * (tx & 3) + j : tx + 32 * j; };
+        constexpr int NI = 8, NJ = 4;
+        auto row_of = [&](int i) { return ty + 16 * i; };
+        auto col_of = [&](int j) { return tx + 32 * j; };
         int acc[NI][NJ];
 #pragma unroll
         for (int i = 0; i < NI; ++i)
@@ -1400,11 +1403,16 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
     const int lane = threadIdx.x & 31;
     const unsigned long long warp_id = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long base = warp_id * 32; base < n; base += n_warps * 32) {
+    // a warp's candidates are worked through one after the other, so a lone batch of 32 is the kernel's minimum time:
+    // when there are fewer candidates than 32 per warp (multi-GPU shares, small inputs) the batches shrink so that
+    // every warp gets some.  (Equalising larger loads the same way was measured slower, see below.)
+    const unsigned long long per_warp = (n + n_warps - 1) / n_warps;
+    const unsigned long long batch = per_warp < 32 ? (per_warp ? per_warp : 1) : 32;
+    for (unsigned long long base = warp_id * batch; base < n; base += n_warps * batch) {
         const unsigned long long c = base + lane;
         int ra = 0, rb = 0;
         bool keep = false;
-        if (c < n) {
+        if ((unsigned long long)lane < batch && c < n) {
             const uint2 pr = cand[c];
             ra = permA[pr.x];
             rb = permB[pr.y];

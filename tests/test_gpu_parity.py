@@ -178,6 +178,46 @@ def test_cardinalities_beyond_the_sort_key_clamp():
     assert want.tolist() == [0, 0, 0, 3, 3, 3, 6]
 
 
+def _near_duplicate_rows(n, card, n_cols, seed, spread):
+    """rows of (almost) equal cardinality, planted in families whose members differ by a few columns"""
+    rng = np.random.default_rng(seed)
+    rows = []
+    while len(rows) < n:
+        base = set(rng.choice(n_cols, size=card, replace=False).tolist())
+        for _ in range(int(rng.integers(1, 6))):
+            r = set(base)
+            for _ in range(int(rng.integers(0, 3))):          # swap a column: distance 2, same cardinality
+                r.remove(next(iter(r)))
+                r.add(int(rng.integers(n_cols)))
+            for _ in range(int(rng.integers(0, spread + 1))):  # add a column: distance 1, cardinality + 1
+                r.add(int(rng.integers(n_cols)))
+            rows.append(sorted(r))
+    return rows[:n]
+
+
+@pytest.mark.parametrize("max_dist", [1, 2, 3])
+@pytest.mark.parametrize("spread", [0, 2])
+def test_two_key_schedule_on_equal_cardinalities(max_dist, spread):
+    """every tile holds rows of one cardinality (spread 0) or of a few: the (cardinality, half-cardinality) runs of
+    k_schedule decide which tile pairs are evaluated at all — no edge may be lost, for the triangle and the rectangle"""
+    rows = _near_duplicate_rows(3000, 40, 5000, seed=7 + spread, spread=spread)
+    indptr, indices, n_cols = rows_to_csr(rows, 5000)
+    want, want_edges = oracle.cluster(indptr, indices, max_dist)
+    for bits in (128, 256, 512):
+        with _native.Context(sketch_bits=bits, want_edges=1) as ctx:
+            ctx.upload_csr(indptr, indices, n_cols)
+            st = ctx.run_sync(max_dist)
+            assert np.array_equal(ctx.download_labels(), want)
+            assert st.n_edges == want_edges
+            if bits <= 256 and spread == 0:   # the runs prune: fewer tile pairs than the triangle of all tiles
+                tiles = (len(rows) + 127) // 128
+                assert st.pairs_evaluated < tiles * (tiles + 1) // 2 * 128 * 128
+    query = np.arange(0, len(rows), 7, dtype=np.int32)
+    src, dst, _ = _native.neighbours_csr(indptr, indices, n_cols, max_dist, query_rows=query)
+    ws, wd = oracle.edges(indptr, indices, max_dist, queries=query)
+    assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("max_dist", [1, 2])
 def test_incremental_rectangle_matches_oracle(max_dist, engine):
