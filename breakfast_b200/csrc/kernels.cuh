@@ -511,8 +511,8 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
 // every row its sketch (row-major staging, 4*WORDS bytes per row) AND its sort key c << 16 | s (see K2).
 // A block takes 128 consecutive rows - one contiguous stretch of `indices`.  Rows are short (about 90 columns), so a
 // warp folds FOUR rows at a time, eight lanes each: every lane XORs the bits of its columns straight into the row's
-// sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction; one ATOMS.ADD more
-// for the columns of H), four loads per lane in flight.  Reads 4*nnz + 8*N bytes, writes N*(m/8 + 8) bytes.
+// sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction; the columns of H are
+// counted in a register), eight loads per lane in flight.  Reads 4*nnz + 8*N bytes, writes N*(m/8 + 8) bytes.
 // (Measured alternatives at 1 M rows of ~89 columns: a warp per row with per-lane word selects + redux.sync and
 // lane-0 stores: 0.34 ms, in sorted (gather) or storage order alike; a thread per row: 0.69 ms, its 32-sector
 // loads are L1-wavefront bound; the shared-memory form: 0.13 ms.)
@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         for (int t = 0; t < WORDS; ++t) sk[threadIdx.x][t] = 0u;
     }
     __syncthreads();
+    constexpr int PACK_LOADS = 8;   // independent loads per lane before the first use
     const int sg = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
     for (int k = 0; k < TILE / 32; ++k) {
@@ -547,12 +548,12 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         const int64_t e = row_e[row];
         uint32_t* dst = sk[row];
         uint32_t in_h = 0;   // this lane's columns in H = those with the top hash bit set
-        for (int64_t q = row_b[row] + l8; q < e; q += 32) {
-            int32_t col[4];
+        for (int64_t q = row_b[row] + l8; q < e; q += 8 * PACK_LOADS) {
+            int32_t col[PACK_LOADS];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) col[t] = q + 8 * t < e ? __ldg(&indices[q + 8 * t]) : -1;
+            for (int t = 0; t < PACK_LOADS; ++t) col[t] = q + 8 * t < e ? __ldg(&indices[q + 8 * t]) : -1;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < PACK_LOADS; ++t) {
                 if (col[t] >= 0) {   // column ids are non-negative
                     const uint32_t h = fold_hash((uint32_t)col[t], log2m);
                     atomicXor(&dst[h >> 5], 1u << (h & 31));
@@ -1130,6 +1131,8 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
         int mxj[L1_GROUP];
 #pragma unroll
         for (int jt = 0; jt < L1_GROUP; ++jt) {
+            mxj[jt] = -64;
+            if (jt >= cnt) continue;   // warp-uniform: a partly filled item does not pay for its missing tiles
             int mh[2];
 #pragma unroll
             for (int hgrp = 0; hgrp < 2; ++hgrp) {
