@@ -18,7 +18,7 @@
 // Other forms: k_card_keys + k_pack_sketch / k_pack_full (wider sketches, FULL engine), k_pairs<K4> (single-kernel
 // tiled XOR/POPC + threshold + compaction), k_pairs_l1 + k_pairs_l2 (level 1 on the integer pipes).
 //
-// Bitset layout in HBM ("tile-blocked"): rows are in cardinality-sorted order, grouped in tiles of
+// Bitset layout in HBM ("tile-blocked"): rows are in sort-key order (K2), grouped in tiles of
 // TILE=128 rows.  A row's bitset is cut into chunks of 4*K4 32-bit words (K4 = 16-byte groups per
 // chunk, K4 in {1,2,4}).  One (tile, chunk) block is contiguous:
 //       uint4 blk[K4][128]   blk[k4][row] = words 4*k4 .. 4*k4+3 of that row's chunk
@@ -1447,42 +1447,60 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                     // precede it), so matching A[k] against B[k-d..k+d] finds every common column; if the
                     // distance is larger the count can only be too small, i.e. the pair is still rejected.
                     // No data-dependent addressing.
-                    if (DWIN > 0 && lb <= 4 * 32) {
-                        // Rows of up to 128 columns (nearly all): each lane loads its <= 4 columns of either row once
-                        // (positions lane + 32 s; all eight loads independent and issued back to back, so a candidate
-                        // costs about one memory round trip) and gets the +-DWIN neighbours of B from lane rotations
-                        // instead of more loads.  (Equalising the batches over the warps - 26 candidates in each of three
-                        // rounds instead of 32/32/0-or-32 at 1 M rows - was measured slower, 289 vs 238 us: the scattered
-                        // row reads run at about 2.4 TB/s and more warps in flight do not raise that.)
+                    if (DWIN > 0) {
+                        // The rows are worked through in chunks of 128 columns (one chunk for nearly all rows): each lane
+                        // loads its <= 4 columns of either row once (positions base + lane + 32 s; all loads of a chunk
+                        // independent and issued back to back, so a chunk costs about one memory round trip) and gets the
+                        // +-DWIN neighbours of B from lane rotations instead of more loads; the DWIN columns of B just
+                        // outside the chunk come from two small halo loads.  (Equalising the batches over the warps - 26
+                        // candidates in each of three rounds instead of 32/32/0-or-32 at 1 M rows - was measured slower,
+                        // 289 vs 238 us: the scattered row reads run at about 2.4 TB/s and more warps in flight do not
+                        // raise that.)
+                        constexpr int NW = DWIN > 0 ? DWIN : 1;
                         const int32_t* pa = indices + ia;
                         const int32_t* pb = indices + ib;
-                        const int la32 = (int)la, lb32 = (int)lb;
-                        int av[4], bv[4];
+                        const int la32 = (int)la, lb32 = (int)lb;   // a row has fewer than 2^31 columns
+                        for (int base = 0; base < la32; base += 128) {
+                            int av[4], bv[4];
 #pragma unroll
-                        for (int sw = 0; sw < 4; ++sw) {
-                            const int k = lane + 32 * sw;
-                            av[sw] = k < la32 ? __ldg(pa + k) : -2;   // column ids are >= 0: the fillers match nothing
-                            bv[sw] = k < lb32 ? __ldg(pb + k) : -1;
-                        }
-                        constexpr int NW = DWIN > 0 ? DWIN : 1;
-                        int dn[4][NW], up[4][NW];   // bv[sw] rotated by -o / +o lanes
+                            for (int sw = 0; sw < 4; ++sw) {
+                                const int k = base + lane + 32 * sw;
+                                av[sw] = k < la32 ? __ldg(pa + k) : -2;   // column ids are >= 0: the fillers match nothing
+                                bv[sw] = k < lb32 ? __ldg(pb + k) : -1;
+                            }
+                            // halo: lane t < NW holds B[base - NW + t] and B[base + 128 + t]
+                            int halo_lo = -1, halo_hi = -1;
+                            if (lane < NW) {
+                                if (base - NW + lane >= 0) halo_lo = __ldg(pb + base - NW + lane);
+                                if (base + 128 + lane < lb32) halo_hi = __ldg(pb + base + 128 + lane);
+                            }
+                            int dn[4][NW], up[4][NW];   // bv[sw] rotated by -o / +o lanes
 #pragma unroll
-                        for (int sw = 0; sw < 4; ++sw)
+                            for (int sw = 0; sw < 4; ++sw)
+#pragma unroll
+                                for (int o = 1; o <= NW; ++o) {
+                                    dn[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane - o) & 31);
+                                    up[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane + o) & 31);
+                                }
+                            // lane < o of the first sweep needs B[base + lane - o] = halo_lo of lane NW + lane - o;
+                            // lane >= 32 - o of the last sweep needs B[base + 128 + lane + o - 32] = halo_hi of that lane
+                            int hlo[NW], hhi[NW];
 #pragma unroll
                             for (int o = 1; o <= NW; ++o) {
-                                dn[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane - o) & 31);
-                                up[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane + o) & 31);
+                                hlo[o - 1] = __shfl_sync(0xffffffffu, halo_lo, (NW + lane - o) & 31);
+                                hhi[o - 1] = __shfl_sync(0xffffffffu, halo_hi, (lane + o) & 31);
                             }
 #pragma unroll
-                        for (int sw = 0; sw < 4; ++sw) {
-                            bool hit = av[sw] == bv[sw];
+                            for (int sw = 0; sw < 4; ++sw) {
+                                bool hit = av[sw] == bv[sw];
 #pragma unroll
-                            for (int o = 1; o <= NW; ++o) {
-                                const int below = lane >= o ? dn[sw][o - 1] : (sw > 0 ? dn[sw - 1][o - 1] : -1);        // B[k - o]
-                                const int above = lane + o < 32 ? up[sw][o - 1] : (sw < 3 ? up[sw + 1][o - 1] : -1);   // B[k + o]
-                                hit |= (av[sw] == below) | (av[sw] == above);
+                                for (int o = 1; o <= NW; ++o) {
+                                    const int below = lane >= o ? dn[sw][o - 1] : (sw > 0 ? dn[sw - 1][o - 1] : hlo[o - 1]);        // B[k - o]
+                                    const int above = lane + o < 32 ? up[sw][o - 1] : (sw < 3 ? up[sw + 1][o - 1] : hhi[o - 1]);   // B[k + o]
+                                    hit |= (av[sw] == below) | (av[sw] == above);
+                                }
+                                inter += hit ? 1 : 0;
                             }
-                            inter += hit ? 1 : 0;
                         }
                     } else {
                         for (int64_t k = lane; k < la; k += 32) {

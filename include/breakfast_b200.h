@@ -66,11 +66,13 @@ typedef struct bf_stats {
     int64_t pairs_band;       /* candidate pairs: ||A|-|B|| <= max_dist    */
     int64_t pairs_evaluated;  /* pairs the tile kernel evaluated on this rank (incl. tile padding) */
     int64_t tiles_total;      /* tile pairs of the whole (upper-triangular) tile space */
-    int64_t tiles_band;       /* tile pairs surviving cardinality-band pruning         */
+    int64_t tiles_band;       /* tile pairs left by the band pruning on (|A|, |A n H|) */
     int64_t tiles_rank;       /* of those, processed by this rank                      */
     int64_t n_candidates;     /* sketch survivors handed to the exact verify kernel    */
     int64_t n_edges;          /* verified edges (d <= max_dist), this rank             */
     int64_t n_components;     /* after the last union-find/merge                       */
+    /* device time of the phases of the last run.  128/256-bit sketches: ms_sort = sketch + sort-key pass over the
+       columns and the radix sort, ms_pack = sorted tile layouts; other forms: ms_sort = keys + sort, ms_pack = bit-pack */
     double ms_h2d, ms_sort, ms_pack, ms_pairs, ms_verify, ms_cc, ms_merge, ms_d2h, ms_total;
     /* accumulated over every bf_run since the previous bf_sync (at most the last 256 runs): */
     int64_t runs_since_sync;  /* how many bf_run calls these sums cover                        */

@@ -197,10 +197,13 @@ def _near_duplicate_rows(n, card, n_cols, seed, spread):
 
 @pytest.mark.parametrize("max_dist", [1, 2, 3])
 @pytest.mark.parametrize("spread", [0, 2])
-def test_two_key_schedule_on_equal_cardinalities(max_dist, spread):
+@pytest.mark.parametrize("card", [40, 600])
+def test_two_key_schedule_on_equal_cardinalities(max_dist, spread, card):
     """every tile holds rows of one cardinality (spread 0) or of a few: the (cardinality, half-cardinality) runs of
-    k_schedule decide which tile pairs are evaluated at all — no edge may be lost, for the triangle and the rectangle"""
-    rows = _near_duplicate_rows(3000, 40, 5000, seed=7 + spread, spread=spread)
+    k_schedule decide which tile pairs are evaluated at all — no edge may be lost, for the triangle and the rectangle.
+    card 600: both key halves need their high byte (all four radix passes run) and the rows are longer than the
+    128 columns the verify kernel handles in registers."""
+    rows = _near_duplicate_rows(3000 if card < 100 else 1500, card, 5000, seed=7 + spread, spread=spread)
     indptr, indices, n_cols = rows_to_csr(rows, 5000)
     want, want_edges = oracle.cluster(indptr, indices, max_dist)
     for bits in (128, 256, 512):
