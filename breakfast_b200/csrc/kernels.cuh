@@ -512,7 +512,7 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
 // A block takes 128 consecutive rows - one contiguous stretch of `indices`.  Rows are short (about 90 columns), so a
 // warp folds FOUR rows at a time, eight lanes each: every lane XORs the bits of its columns straight into the row's
 // sketch in shared memory (one ATOMS.XOR per column - no per-word selects, no warp reduction; the columns of H are
-// counted in a register), eight loads per lane in flight.  Reads 4*nnz + 8*N bytes, writes N*(m/8 + 8) bytes.
+// counted in a register), six loads per lane in flight.  Reads 4*nnz + 8*N bytes, writes N*(m/8 + 8) bytes.
 // (Measured alternatives at 1 M rows of ~89 columns: a warp per row with per-lane word selects + redux.sync and
 // lane-0 stores: 0.34 ms, in sorted (gather) or storage order alike; a thread per row: 0.69 ms, its 32-sector
 // loads are L1-wavefront bound; the shared-memory form: 0.13 ms.)
@@ -540,18 +540,20 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         for (int t = 0; t < WORDS; ++t) sk[threadIdx.x][t] = 0u;
     }
     __syncthreads();
-    constexpr int PACK_LOADS = 8;   // independent loads per lane before the first use
+    constexpr int PACK_LOADS = 6;   // independent loads per lane before the first use (48 columns per row and round:
+                                    // two rounds cover 96, the kernel is bound by issued instructions, ncu 76 %)
     const int sg = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
     for (int k = 0; k < TILE / 32; ++k) {
         const int row = warp * (TILE / 8) + 4 * k + sg;
-        const int64_t e = row_e[row];
+        const int32_t* src = indices + row_b[row];
+        const int len = (int)(row_e[row] - row_b[row]);   // a row has fewer than 2^31 columns
         uint32_t* dst = sk[row];
         uint32_t in_h = 0;   // this lane's columns in H = those with the top hash bit set
-        for (int64_t q = row_b[row] + l8; q < e; q += 8 * PACK_LOADS) {
+        for (int q = l8; q < len; q += 8 * PACK_LOADS) {
             int32_t col[PACK_LOADS];
 #pragma unroll
-            for (int t = 0; t < PACK_LOADS; ++t) col[t] = q + 8 * t < e ? __ldg(&indices[q + 8 * t]) : -1;
+            for (int t = 0; t < PACK_LOADS; ++t) col[t] = q + 8 * t < len ? __ldg(src + q + 8 * t) : -1;
 #pragma unroll
             for (int t = 0; t < PACK_LOADS; ++t) {
                 if (col[t] >= 0) {   // column ids are non-negative
