@@ -740,7 +740,9 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         if (max_dist == 1) verify = k_verify_unite<1>;
         else if (max_dist == 2) verify = k_verify_unite<2>;
         else if (max_dist == 3) verify = k_verify_unite<3>;
-        verify<<<c->num_sms * 8, 256, 0, c->stream>>>(
+        int vbps = 0;   // grid-stride kernel: launch exactly the blocks that are resident at once
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, verify, 256, 0));
+        verify<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
             c->cand.as<uint2>(), c->cand_cap_used, valsA[0].as<int32_t>(), c->valsB[0].as<int32_t>(),
             c->d_indptr, c->d_indices, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
             c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
