@@ -162,8 +162,8 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
     ap.add_argument("--engine", default="sketch", choices=["sketch", "full"])
