@@ -212,17 +212,17 @@ class Context:
         return st
 
     def run_sync(self, max_dist: int, rank: int = 0, world: int = 1) -> Stats:
-        """run + sync, growing the candidate buffer when it overflows."""
-        for _ in range(3):
+        """run + sync; on BF_ERR_OVERFLOW bf_sync has raised the capacity of whatever overflowed (work list, level-2
+        queue, candidate buffer - one can follow the other), so the pass is simply run again."""
+        for _ in range(6):
             self.run(max_dist, rank, world)
             st = Stats()
             rc = self._lib.bf_sync(self._h, C.byref(st))
             if rc == BF_ERR_OVERFLOW:
-                self.set_option("cand_capacity", st.n_candidates + st.n_candidates // 4 + 1024)
                 continue
             _ck(rc)
             return st
-        raise NativeError(BF_ERR_OVERFLOW, "candidate buffer overflow persisted")
+        raise NativeError(BF_ERR_OVERFLOW, "buffer overflow persisted")
 
     def labels_to_device(self, device_ptr: int):
         _ck(self._lib.bf_labels_to_device(self._h, C.c_void_p(device_ptr)))

@@ -915,29 +915,32 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
     }
     c->runs_since_sync = 0;
     c->launches_since_sync = 0;
-    if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
-        char buf[256];
-        // level1 = 1 cuts the queue into one segment per CTA: the fullest segment decides
-        const unsigned long long seg_need = c->level1 == 1 ? (unsigned long long)h.seg_max * (unsigned long long)c->num_sms : 0;
-        if (h.n_units > c->queue_cap_used || seg_need > c->queue_cap_used) {
-            const unsigned long long need = std::max<unsigned long long>(h.n_units, seg_need);
-            c->units_capacity = (int64_t)(need + need / 4 + 1024 + c->num_sms);
-            snprintf(buf, sizeof buf, "level-2 queue overflow: %llu units > capacity %llu; units_capacity raised, run again",
-                     (unsigned long long)h.n_units, c->queue_cap_used);
-            return fail(BF_ERR_OVERFLOW, buf);
+    // Every bounded buffer is checked here; whatever overflowed is given the capacity this pass asked for (a later
+    // buffer of the chain may have seen only part of its input, so another round can follow) and the caller reruns.
+    {
+        std::string what;
+        char buf[200];
+        if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
+            if (nwork > c->items_cap_used) {
+                c->items_capacity = (int64_t)(nwork + 1024);
+                snprintf(buf, sizeof buf, "work list: %llu items > capacity %llu; ", (unsigned long long)nwork, c->items_cap_used);
+                what += buf;
+            }
+            // level1 = 1 cuts the queue into one segment per CTA: the fullest segment decides
+            const unsigned long long seg_need = c->level1 == 1 ? (unsigned long long)h.seg_max * (unsigned long long)c->num_sms : 0;
+            if (h.n_units > c->queue_cap_used || seg_need > c->queue_cap_used) {
+                const unsigned long long need = std::max<unsigned long long>(h.n_units, seg_need);
+                c->units_capacity = (int64_t)(need + need / 4 + 1024 + c->num_sms);
+                snprintf(buf, sizeof buf, "level-2 queue: %llu units > capacity %llu; ", (unsigned long long)h.n_units, c->queue_cap_used);
+                what += buf;
+            }
         }
-        if (nwork > c->items_cap_used) {
-            c->items_capacity = (int64_t)(nwork + 1024);
-            snprintf(buf, sizeof buf, "work list overflow: %llu items > capacity %llu; items_capacity raised, run again",
-                     (unsigned long long)nwork, c->items_cap_used);
-            return fail(BF_ERR_OVERFLOW, buf);
+        if (overflow) {
+            c->cand_capacity = std::max<int64_t>(c->cand_capacity, (int64_t)(h.n_cand + h.n_cand / 4 + 1024));
+            snprintf(buf, sizeof buf, "candidate buffer: %llu candidates > capacity %llu; ", (unsigned long long)h.n_cand, c->cand_cap_used);
+            what += buf;
         }
-    }
-    if (overflow) {
-        char buf[256];
-        snprintf(buf, sizeof buf, "candidate buffer overflow: %llu candidates > capacity %llu; set cand_capacity and run again",
-                 (unsigned long long)h.n_cand, c->cand_cap_used);
-        return fail(BF_ERR_OVERFLOW, buf);
+        if (!what.empty()) return fail(BF_ERR_OVERFLOW, "overflow - " + what + "capacities raised, run again");
     }
     return BF_OK;
 }
@@ -991,18 +994,15 @@ int bf_download_edges(bf_ctx* c, int32_t* src_out, int32_t* dst_out) {
 // ------------------------------------------------------------------------------------------------
 static int run_with_retry(bf_ctx* c, int32_t max_dist, bf_stats* st) {
     bf_stats local;
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 6; ++attempt) {   // work list -> queue -> candidates can overflow one after the other
         TRY(bf_run(c, max_dist, 0, 1));
         int rc = bf_sync(c, &local);
-        if (rc == BF_ERR_OVERFLOW) {
-            c->cand_capacity = local.n_candidates + local.n_candidates / 4 + 1024;
-            continue;
-        }
+        if (rc == BF_ERR_OVERFLOW) continue;   // bf_sync raised the capacities
         if (rc != BF_OK) return rc;
         if (st) *st = local;
         return BF_OK;
     }
-    return fail(BF_ERR_OVERFLOW, "candidate buffer overflow persisted after retries");
+    return fail(BF_ERR_OVERFLOW, "buffer overflow persisted after retries");
 }
 
 int bf_cluster_csr(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols, int32_t max_dist,

@@ -41,7 +41,7 @@ typedef enum bf_status {
     BF_ERR_NO_DEVICE = -2,    /* no usable CUDA device (there is no CPU fallback)     */
     BF_ERR_CUDA = -3,         /* a CUDA runtime call failed; see bf_last_error()      */
     BF_ERR_OOM = -4,          /* device or host allocation failed                     */
-    BF_ERR_OVERFLOW = -5,     /* candidate/edge buffer too small (async API only)     */
+    BF_ERR_OVERFLOW = -5,     /* a bounded device buffer was too small (async API only): bf_sync raised its capacity, run again */
     BF_ERR_STATE = -6         /* call order violated (e.g. run before upload)         */
 } bf_status;
 
@@ -146,8 +146,9 @@ int bf_merge_labels_host(bf_ctx* ctx, const int32_t* gathered_host, int32_t worl
  * breakfast.py:304,93-113).  CSR of lists on the host. Unions into current labels. */
 int bf_union_lists(bf_ctx* ctx, const int64_t* list_indptr, const int32_t* list_members,
                    int64_t n_lists);
-/* Wait for the stream, read counters/timers; BF_ERR_OVERFLOW if the candidate
- * buffer was too small (grow "cand_capacity" and run again). */
+/* Wait for the stream, read counters/timers.  BF_ERR_OVERFLOW: a bounded device buffer (work list, level-2
+ * queue, candidate/edge buffer) was too small for this input; its capacity has been raised - call bf_run again
+ * (a later buffer of the chain may overflow in turn; the one-shot entry points below retry by themselves). */
 int bf_sync(bf_ctx* ctx, bf_stats* stats_out);
 int bf_download_labels(bf_ctx* ctx, int32_t* labels_out /* [n_rows] */);
 /* Edge list of the last run (needs option want_edges=1): original row indices. */

@@ -347,6 +347,24 @@ def test_candidate_overflow_is_reported_and_recovered():
         assert np.array_equal(ctx.download_labels(), want)
 
 
+@pytest.mark.parametrize("option", ["units_capacity", "items_capacity"])
+def test_queue_and_work_list_overflow_are_recovered(option):
+    """the level-2 queue and the work list are bounded too: bf_sync reports the overflow, raises the capacity, and the
+    rerun (which may have to grow the next buffer of the chain as well) gives the exact result"""
+    indptr, indices, n_cols = synth.generate(6000, seed=8).csr()
+    want, want_edges = oracle.cluster(indptr, indices, 2)
+    with _native.Context(want_edges=1, cand_capacity=64, **{option: 8}) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        ctx.run(2)
+        with pytest.raises(_native.NativeError) as e:
+            ctx.sync()
+        assert e.value.code == _native.BF_ERR_OVERFLOW
+        st = ctx.run_sync(2)
+        assert st.n_edges == want_edges and np.array_equal(ctx.download_labels(), want)
+    labels, st = _native.cluster_csr(indptr, indices, n_cols, 2)
+    assert np.array_equal(labels, want)
+
+
 def test_call_order_and_argument_errors():
     with _native.Context() as ctx:
         with pytest.raises(_native.NativeError) as e:
