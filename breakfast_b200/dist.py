@@ -48,8 +48,35 @@ class RankRunner:
         self.ctx.run(max_dist, self.rank, self.world)
         if self.world > 1:
             self.ctx.labels_to_device(self.local.data_ptr())
-            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+            if self.local.is_cuda:
+                dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+            else:   # gloo (CPU tests of the host logic)
+                dist.all_gather(list(self.gathered.unbind(0)), self.local, group=self.group)
             self.ctx.merge_labels_device(self.gathered.data_ptr(), self.world)
+
+    def run_sync(self, max_dist: int, attempts: int = 6):
+        """One synchronous pass on every rank; returns this rank's counters.  A rank whose bounded device buffers
+        overflowed (bf_sync has raised their capacity) must run again - and because the label exchange is a collective,
+        so must every other rank: the overflow flag is max-reduced over the group before anyone decides."""
+        import torch
+        import torch.distributed as dist
+        from . import _native
+        for _ in range(attempts):
+            self.step(max_dist)
+            st, over = None, 0
+            try:
+                st = self.ctx.sync()
+            except _native.NativeError as e:
+                if e.code != _native.BF_ERR_OVERFLOW:
+                    raise
+                over = 1
+            if self.world > 1:
+                flag = torch.tensor([over], dtype=torch.int32, device=self.local.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+                over = int(flag.item())
+            if not over:
+                return st
+        raise _native.NativeError(_native.BF_ERR_OVERFLOW, "buffer overflow persisted on some rank")
 
 
 class ShardedCsrUploader:
