@@ -178,6 +178,22 @@ def test_cardinalities_beyond_the_sort_key_clamp():
     assert want.tolist() == [0, 0, 0, 3, 3, 3, 6]
 
 
+@pytest.mark.parametrize("max_dist", [1, 2, 3])
+def test_schedule_counter_matches_the_cpu_mirror(max_dist):
+    """k_schedule lists exactly the tile pairs that tools/schedule_sim.py (its CPU restatement, whose soundness
+    tests/test_schedule_math.py checks against the oracle) lists"""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import schedule_sim
+    indptr, indices, n_cols = synth.generate(20000, seed=13).csr()
+    with _native.Context(sketch_bits=128) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(max_dist)
+    assert st.tiles_band == schedule_sim.tile_pairs(indptr, indices, max_dist, 2)
+    assert st.tiles_band < schedule_sim.tile_pairs(indptr, indices, max_dist, 1)
+
+
 def _near_duplicate_rows(n, card, n_cols, seed, spread):
     """rows of (almost) equal cardinality, planted in families whose members differ by a few columns"""
     rng = np.random.default_rng(seed)

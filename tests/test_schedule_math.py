@@ -29,3 +29,29 @@ def test_partner_interval_of_the_second_key(d):
     # outside the cardinality band nothing is feasible
     for D in (-d - 1, d + 1):
         assert not [ds for ds in range(-3 * d - 2, 3 * d + 3) if abs(ds) + abs(D - ds) <= d]
+
+
+@pytest.mark.parametrize("max_dist", [1, 2, 3])
+@pytest.mark.parametrize("n_keys", [1, 2, 3])
+def test_schedule_mirror_loses_no_edge(max_dist, n_keys):
+    """tools/schedule_sim.py restates k_schedule on the CPU (the GPU suite pins the kernel's tile-pair counter to it):
+    every edge the oracle finds must lie in a tile pair the schedule lists, and more keys never list more pairs"""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import oracle
+    import schedule_sim
+    from breakfast_b200 import synth
+    indptr, indices, _ = synth.generate(6000, seed=11).csr()
+    order, runs = schedule_sim.schedule(indptr, indices, max_dist, n_keys)
+    pos = np.empty(len(order), dtype=np.int64)
+    pos[order] = np.arange(len(order))
+    covered = set()
+    for tile, first, end in runs:
+        covered.update((tile, j) for j in range(first, end))
+    src, dst = oracle.edges(indptr, indices, max_dist)
+    assert src.size > 100
+    a, b = np.minimum(pos[src], pos[dst]) // 128, np.maximum(pos[src], pos[dst]) // 128
+    assert all((int(i), int(j)) in covered for i, j in zip(a, b))
+    if n_keys > 1:
+        assert len(covered) <= schedule_sim.tile_pairs(indptr, indices, max_dist, n_keys - 1)
