@@ -4,6 +4,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl refer
 this package; it is the checker, never the product.  breakfast_b200 does not import it.
 
   oracle.c       plain-C restatement of the distance + threshold + components core
+  hashjoin.py    second, independent oracle for max_dist <= 2 at full scale (deletion-neighbourhood hash joins,
+                 every match verified exactly)
   ref_port.py    Python restatement of the whole reference pipeline, structured like the reference
                  (per-cardinality batches through scikit-learn's pairwise_distances_chunked, networkx
                  components), used as the CPU baseline ("port")
@@ -50,6 +52,10 @@ def _load():
         lib.orc_components.argtypes = [i64, vp, vp, i64, vp, vp, i64, vp]
         lib.orc_cluster.restype = i64
         lib.orc_cluster.argtypes = [vp, vp, i64, i32, vp]
+        lib.orc_within_batch.restype = None
+        lib.orc_within_batch.argtypes = [vp, vp, vp, vp, i64, i64, vp]
+        lib.orc_join_two_deletions.restype = i64
+        lib.orc_join_two_deletions.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(vp)]
         _lib = lib
     return _lib
 

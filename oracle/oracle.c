@@ -168,3 +168,78 @@ int64_t orc_cluster(const int64_t* indptr, const int32_t* indices, int64_t n, in
     free(s); free(d);
     return rc ? -1 : ne;
 }
+
+/* ---- helpers of oracle/hashjoin.py (the second, hash-join oracle) ------------------------------------------- */
+
+/* ok_out[k] = (|A_src[k] xor A_dst[k]| <= limit), for m pairs */
+void orc_within_batch(const int64_t* indptr, const int32_t* indices, const int32_t* src, const int32_t* dst, int64_t m,
+                      int64_t limit, unsigned char* ok_out) {
+#pragma omp parallel for schedule(static, 1024)
+    for (int64_t k = 0; k < m; ++k) {
+        const int64_t a = src[k], b = dst[k];
+        ok_out[k] = symdiff(indices + indptr[a], indptr[a + 1] - indptr[a], indices + indptr[b],
+                            indptr[b + 1] - indptr[b], limit) <= limit;
+    }
+}
+
+/* Candidates of the "superset by two columns" case: all (A, B) with H[A] - g[x] - g[y] == H[B] for some columns x < y
+ * of A and |B| == |A| - 2.  g[] = per-entry column hashes (aligned with indices), row_hash[] = their row sums (mod 2^64).
+ * sorted_hash[] / sorted_row[] = the rows ordered by hash; table = bitset over the low `table_bits` bits of every row
+ * hash (rejects almost every key with one lookup).  Hash collisions may add candidates, never lose one; the caller
+ * verifies.  Returns the candidate count (-1 on allocation failure); *a_out / *b_out are malloc'ed. */
+int64_t orc_join_two_deletions(const int64_t* indptr, const uint64_t* g, const uint64_t* row_hash, int64_t n,
+                               const uint64_t* sorted_hash, const int32_t* sorted_row, const uint64_t* table,
+                               int32_t table_bits, int32_t** a_out, int32_t** b_out) {
+    const uint64_t mask = (table_bits >= 64) ? ~0ull : ((1ull << table_bits) - 1ull);
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    edge_vec* vecs = (edge_vec*)calloc((size_t)nthreads, sizeof *vecs);
+    if (!vecs) return -1;
+    int failed = 0;
+#pragma omp parallel
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        edge_vec* v = &vecs[t];
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < n; ++r) {
+            const int64_t b0 = indptr[r], len = indptr[r + 1] - b0;
+            for (int64_t i = 0; i + 1 < len; ++i) {
+                const uint64_t hi = row_hash[r] - g[b0 + i];
+                for (int64_t j = i + 1; j < len; ++j) {
+                    const uint64_t key = hi - g[b0 + j];
+                    const uint64_t slot = key & mask;
+                    if (!((table[slot >> 6] >> (slot & 63)) & 1ull)) continue;
+                    int64_t lo = 0, up = n; /* first sorted position with hash >= key */
+                    while (lo < up) {
+                        const int64_t mid = (lo + up) >> 1;
+                        if (sorted_hash[mid] < key) lo = mid + 1; else up = mid;
+                    }
+                    for (int64_t p = lo; p < n && sorted_hash[p] == key; ++p) {
+                        const int64_t c = sorted_row[p];
+                        if (indptr[c + 1] - indptr[c] == len - 2 && push(v, (int32_t)r, (int32_t)c)) failed = 1;
+                    }
+                }
+            }
+        }
+    }
+    int64_t total = 0;
+    for (int t = 0; t < nthreads; ++t) total += vecs[t].n;
+    int32_t* a = (int32_t*)malloc((size_t)(total > 0 ? total : 1) * sizeof *a);
+    int32_t* b = (int32_t*)malloc((size_t)(total > 0 ? total : 1) * sizeof *b);
+    if (!a || !b) failed = 1;
+    if (!failed) {
+        int64_t off = 0;
+        for (int t = 0; t < nthreads; ++t)
+            for (int64_t k = 0; k < vecs[t].n; ++k, ++off) { a[off] = vecs[t].e[k].a; b[off] = vecs[t].e[k].b; }
+    }
+    for (int t = 0; t < nthreads; ++t) free(vecs[t].e);
+    free(vecs);
+    if (failed) { free(a); free(b); return -1; }
+    *a_out = a; *b_out = b;
+    return total;
+}

@@ -94,6 +94,12 @@ def test_config3_1m_dist2_mincluster5_8_ranks(million_mult):
         src, dst = ctx.download_edges()
     assert st.pairs_band > 2.5e10 and src.size == st.n_edges
     assert np.array_equal(oracle.components(n, src, dst), single)
+    # the whole edge set, bit for bit, against the second CPU oracle (hash joins + exact verification, about a minute)
+    from oracle import hashjoin
+    hs, hd = hashjoin.edges(indptr, indices, 2)
+    o = np.lexsort((np.maximum(src, dst), np.minimum(src, dst)))
+    assert np.array_equal(np.minimum(src, dst)[o], hs) and np.array_equal(np.maximum(src, dst)[o], hd)
+    assert np.array_equal(single, oracle.components(n, hs, hd))
     rng = np.random.default_rng(3)
     q = np.sort(rng.choice(n, size=800, replace=False)).astype(np.int32)
     ws, wd = oracle.edges(indptr, indices, 2, queries=q)

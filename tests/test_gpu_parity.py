@@ -506,7 +506,7 @@ def test_million_profiles_properties(million):
     # and the WHOLE answer, bit for bit: at max_dist 1 the edge set has a closed form (rows that differ by one
     # column), which the second CPU oracle computes by a hash join + exact verification in seconds
     from oracle import hashjoin
-    ws, wd = hashjoin.edges_d1(indptr, indices, 1)
+    ws, wd = hashjoin.edges(indptr, indices, 1)
     order = np.lexsort((np.maximum(src, dst), np.minimum(src, dst)))
     assert np.array_equal(np.minimum(src, dst)[order], ws) and np.array_equal(np.maximum(src, dst)[order], wd)
     assert np.array_equal(labels, oracle.components(n, ws, wd))
