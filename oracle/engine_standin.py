@@ -42,6 +42,25 @@ class OracleEngine:
         monkeypatch.setattr(engine, "components_incremental", cls.incremental)
 
 
+class HashJoinEngine:
+    """Like OracleEngine.full, but backed by the second oracle (oracle/hashjoin.py, max_dist <= 2): fast enough for
+    the scale goldens (tens of thousands of profiles) on the CPU."""
+
+    @staticmethod
+    def full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None):
+        import oracle
+        from oracle import hashjoin
+        from breakfast_b200.engine import ClusterResult
+        src, dst = hashjoin.edges(indptr, indices, max_dist)
+        labels = oracle.components(len(indptr) - 1, src, dst)
+        return ClusterResult(labels, {}, (src, dst) if want_edges else None)
+
+    @classmethod
+    def install(cls, monkeypatch):
+        from breakfast_b200 import engine
+        monkeypatch.setattr(engine, "components_full", cls.full)
+
+
 def pytest_configure(config):
     from breakfast_b200 import engine
     engine.components_full = OracleEngine.full

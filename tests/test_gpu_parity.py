@@ -462,6 +462,38 @@ def test_measured_pipe_peaks_are_plausible():
     assert _native.measure_peak("lop3") > _native.measure_peak("popc32")
 
 
+# ------------------------------------------------------------------ scale goldens (reference run on 42 k / 67 k sequences)
+@pytest.fixture(scope="module")
+def scale_tables(tmp_path_factory):
+    import hashlib
+    from tests import test_scale_golden as sg
+    root = tmp_path_factory.mktemp("scale_gpu")
+    out = {}
+    for name, recipe in sg.SCALE["tables"].items():
+        text = sg.build_table(recipe)
+        assert hashlib.sha256(text.encode()).hexdigest() == recipe["sha256"]
+        out[name] = root / f"{name}.tsv"
+        out[name].write_text(text)
+    return out
+
+
+def _scale_cases():
+    import json
+    return json.loads((GOLDEN / "scale.json").read_text())["cases"]
+
+
+@pytest.mark.parametrize("case", _scale_cases(), ids=[c["name"] for c in _scale_cases()])
+def test_scale_goldens_through_the_cli(case, scale_tables, tmp_path):
+    """clusters.tsv of the product CLI on the GPU == clusters.tsv the unmodified reference wrote (SHA-256 committed by
+    tests/golden/make_scale_golden.py), on seeded tables of 41 643 / 66 807 sequences: d = 1 and 2, min-cluster-size 5,
+    deletions kept, nextclade notation"""
+    import hashlib
+    from tests import test_scale_golden as sg
+    got = sg.run_case(case, scale_tables[case["table"]], tmp_path)
+    assert got.count("\n") == case["n_lines"]
+    assert hashlib.sha256(got.encode()).hexdigest() == case["sha256"], case["name"]
+
+
 # ------------------------------------------------------------------ BASELINE-size properties (1M profiles)
 @pytest.fixture(scope="module")
 def million():
