@@ -89,3 +89,41 @@ def merge_labels_cpu(gathered: np.ndarray) -> np.ndarray:
 
 
 from oracle.engine_standin import OracleEngine  # noqa: E402,F401  (re-exported for the tests)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scale goldens (tests/golden/scale.json): tables are regenerated from a recipe, only digests are committed
+# ---------------------------------------------------------------------------------------------------------------
+def scale_table(recipe: dict) -> str:
+    """one seeded synthetic table as TSV text"""
+    from breakfast_b200 import synth
+    prof = synth.generate(recipe["n"], seed=recipe["seed"], with_mult=recipe["with_mult"])
+    return prof.table(**recipe["table"]).to_csv(sep="\t", index=False)
+
+
+def scale_chain(recipe: dict) -> list:
+    """three tables for a cached run chain: step 0; step 1 = step 0 minus ~12 % of its sequences (whole profiles
+    disappear -> ghost lists, incl. a planted ghost triple) plus new profiles plus modified sequences, shuffled;
+    step 2 = step 1 minus ~10 % plus more new profiles"""
+    from breakfast_b200 import synth
+    rng = np.random.default_rng(recipe["seed"])
+    df0 = synth.generate(recipe["n"], seed=recipe["seed"], with_mult=True).table("covsonar_dna", " ")
+    a = "C1000T G2000A T3000C A4000G C5000T"
+    ghost = pd.DataFrame({"accession": ["ghostA1", "ghostA2", "ghostX1", "ghostB1", "ghostB2"],
+                          "dna_profile": [a, a, a + " G6000A", a + " G6000A T7000C", a + " G6000A T7000C"]})
+    df0 = pd.concat([df0, ghost], ignore_index=True)
+    ids = df0["accession"].to_numpy()
+    keep = rng.random(len(df0)) > 0.12
+    keep[ids == "ghostX1"] = False
+    keep[np.isin(ids, ["ghostA1", "ghostA2", "ghostB1", "ghostB2"])] = True
+    df1 = df0[keep].copy()
+    extra = synth.generate(recipe["n_new1"], seed=recipe["seed"] + 1, with_mult=True).table("covsonar_dna", " ")
+    extra["accession"] = ["new1_" + s for s in extra["accession"]]
+    mod = rng.choice(len(df1), size=recipe["n_modified"], replace=False)
+    df1.iloc[mod, 1] = [p + " A12345C" if p else "A12345C" for p in df1.iloc[mod, 1]]
+    df1 = pd.concat([df1, extra], ignore_index=True).sample(frac=1.0, random_state=3).reset_index(drop=True)
+    keep2 = rng.random(len(df1)) > 0.10
+    extra2 = synth.generate(recipe["n_new2"], seed=recipe["seed"] + 2, with_mult=False).table("covsonar_dna", " ")
+    extra2["accession"] = ["new2_" + s for s in extra2["accession"]]
+    df2 = pd.concat([extra2, df1[keep2]], ignore_index=True)
+    return [d.to_csv(sep="\t", index=False) for d in (df0, df1, df2)]

@@ -494,6 +494,21 @@ def test_scale_goldens_through_the_cli(case, scale_tables, tmp_path):
     assert hashlib.sha256(got.encode()).hexdigest() == case["sha256"], case["name"]
 
 
+def _scale_chain_cases():
+    import json
+    return json.loads((GOLDEN / "scale.json").read_text())["chain_cases"]
+
+
+@pytest.mark.parametrize("case", _scale_chain_cases(), ids=[c["name"] for c in _scale_chain_cases()])
+def test_scale_cached_chain_through_the_cli(case, tmp_path):
+    """three cached runs (19 k -> 20 k -> 19 k sequences, ghost lists, new x all rectangle on the GPU): every
+    clusters.tsv == what the unmodified reference wrote for the same chain (SHA-256 in scale.json)"""
+    from tests import test_scale_golden as sg
+    steps = sg.write_chain(tmp_path, case["chain"])
+    outs, fresh = sg.run_chain(case, steps, tmp_path)
+    sg.check_chain(case, outs, fresh)
+
+
 # ------------------------------------------------------------------ BASELINE-size properties (1M profiles)
 @pytest.fixture(scope="module")
 def million():
