@@ -64,13 +64,12 @@ def library_path() -> Path:
 
 
 def load() -> C.CDLL:
-    """Load (building in-tree with nvcc if it is absent) the native library."""
+    """Load the native library, (re)building it in-tree with nvcc when it is absent or older than its sources
+    (build.needs_build: a stale library after an edit to kernels.cuh would otherwise be loaded silently)."""
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not path.exists():
-        _build.build()
+    path = _build.build()
     lib = C.CDLL(str(path))
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.bf_abi_version.restype = C.c_int

@@ -213,10 +213,12 @@ def sparse_feature_matrix(features, feature_sep):
 # --------------------------------------------------------------------------------------------
 # clustering
 # --------------------------------------------------------------------------------------------
-def cluster(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache):
+def cluster(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache, pre=None):
+    """`pre` (not in the reference): the CSR dict of hostfast.prepare for exactly these rows, so that the profiles
+    are not tokenised a second time."""
     if max_dist == 0:
         return cluster_identical_features(meta_nodups, min_cluster_size)
-    return cluster_features(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache)
+    return cluster_features(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache, pre=pre)
 
 
 def _assign_cluster_ids(meta, labels, min_cluster_size):
@@ -237,8 +239,7 @@ def _assign_cluster_ids(meta, labels, min_cluster_size):
     return int(kept_roots.sum())
 
 
-def cluster_features(meta, feature_sep, max_dist, min_cluster_size, input_cache, output_cache):
-    pre = meta.attrs.get("bf_csr") if hasattr(meta, "attrs") else None
+def cluster_features(meta, feature_sep, max_dist, min_cluster_size, input_cache, output_cache, pre=None):
     if pre is not None and pre["n"] == len(meta):
         # the native host path (hostfast.prepare) already tokenised the unique profiles
         if pre["n_vocab"] == 0:

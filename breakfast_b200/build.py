@@ -40,18 +40,48 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS + [Path(__file__)])
 
 
+class _BuildLock:
+    """Several processes (torchrun ranks, pytest-xdist workers) may find the library stale at the same time: one
+    builds, the others wait and then see it fresh.  The compiler writes a temporary file that is renamed into place."""
+
+    def __init__(self, target: Path):
+        self.path = target.with_suffix(target.suffix + ".lock")
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+
+
+def _compile(cmd: list, target: Path, what: str) -> None:
+    tmp = target.with_name(f".{target.name}.{os.getpid()}.tmp")
+    res = subprocess.run(cmd + ["-o", str(tmp)], capture_output=True, text=True)
+    if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError(f"{what} failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, target)
+    return res
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in SOURCES] + ["-o", str(LIB_PATH)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+    with _BuildLock(LIB_PATH):
+        if not force and not needs_build():   # another process built it while we waited
+            return LIB_PATH
+        cmd = [_nvcc(), *NVCC_FLAGS]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += [str(s) for s in SOURCES]
+        res = _compile(cmd, LIB_PATH, "nvcc")
+        if verbose:
+            sys.stderr.write(res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -64,10 +94,10 @@ def build_synth(force: bool = False) -> Path:
     if not force and SYNTH_LIB.exists() and SYNTH_LIB.stat().st_mtime >= SYNTH_SRC.stat().st_mtime:
         return SYNTH_LIB
     gcc = shutil.which("gcc") or "gcc"
-    cmd = [gcc, "-O2", "-fPIC", "-shared", "-std=c11", str(SYNTH_SRC), "-o", str(SYNTH_LIB), "-lm"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with _BuildLock(SYNTH_LIB):
+        if not force and SYNTH_LIB.exists() and SYNTH_LIB.stat().st_mtime >= SYNTH_SRC.stat().st_mtime:
+            return SYNTH_LIB
+        _compile([gcc, "-O2", "-fPIC", "-shared", "-std=c11", str(SYNTH_SRC), "-lm"], SYNTH_LIB, "gcc")
     return SYNTH_LIB
 
 
@@ -79,11 +109,13 @@ def build_host(force: bool = False) -> Path:
     """g++ build of the native host-side parser (tokenise / filter / dedup / CSR); no CUDA involved."""
     if not force and HOST_LIB.exists() and HOST_LIB.stat().st_mtime >= HOST_SRC.stat().st_mtime:
         return HOST_LIB
-    gxx = shutil.which("g++") or "g++"
-    cmd = [gxx, "-O2", "-fPIC", "-shared", "-std=c++17", str(HOST_SRC), "-o", str(HOST_LIB)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not found: cannot build libbfhost.so")
+    with _BuildLock(HOST_LIB):
+        if not force and HOST_LIB.exists() and HOST_LIB.stat().st_mtime >= HOST_SRC.stat().st_mtime:
+            return HOST_LIB
+        _compile([gxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-pthread", str(HOST_SRC)], HOST_LIB, "g++")
     return HOST_LIB
 
 

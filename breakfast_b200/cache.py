@@ -32,11 +32,13 @@ def load(input_file, max_dist):
 def save(output_file, neigh, meta, max_dist):
     try:
         print("Export results as pickle")
+        frame = meta[["id", "feature"]]
+        frame.attrs = {}   # the file holds what the reference's holds: no private metadata rides along
         payload = {
             "max_dist": max_dist,
             "version": __version__,
             "neigh": neigh,
-            "meta": meta[["id", "feature"]],
+            "meta": frame,
         }
         output_file.parent.mkdir(parents=True, exist_ok=True)
         with gzip.open(output_file, "wb") as handle:

@@ -95,18 +95,20 @@ def run(input_file, outdir, input_cache, output_cache, id_col, clust_col, var_ty
     os.environ["OMP_NUM_THREADS"] = str(jobs)
 
     meta = breakfast.read_input(input_file, sep, id_col, clust_col)
-    meta_nodups = None
+    meta_nodups, pre = None, None
     if os.environ.get("BREAKFAST_B200_HOST", "native") == "native" and var_type in VAR_TYPES:
         # one native pass (csrc/host_parse.cpp) instead of three Python loops over every token; same result
         from . import hostfast
         if hostfast.available():
-            meta_nodups = hostfast.prepare(meta, sep2, var_type, skip_ins, skip_del, trim_start, trim_end, reference_length)
+            prepared = hostfast.prepare(meta, sep2, var_type, skip_ins, skip_del, trim_start, trim_end, reference_length)
+            if prepared is not None:
+                meta_nodups, pre = prepared
     if meta_nodups is None:
         meta["feature"] = breakfast.filter_features(
             meta["feature"], sep2, var_type, skip_ins, skip_del, trim_start, trim_end, reference_length
         )
         meta_nodups = breakfast.collapse_duplicates(meta)
-    meta_clustered = breakfast.cluster(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache)
+    meta_clustered = breakfast.cluster(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache, pre=pre)
     breakfast.write_output(meta_clustered, meta, outdir)
 
 

@@ -108,7 +108,7 @@ class ShardedCsrUploader:
         self.side = torch.cuda.Stream()
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.free = [None, None]
-        self.next_slot, self.active = 0, None
+        self.next_slot, self.active, self.pending = 0, None, None
 
     def prefetch(self):
         """copy + all-gather the next batch into the idle slot, on the side stream"""
@@ -129,6 +129,9 @@ class ShardedCsrUploader:
     def activate(self):
         """the compute stream waits for the prefetched batch; the context adopts it (no copy)"""
         s = self.pending
+        if s is None:
+            raise RuntimeError("ShardedCsrUploader.activate() without a prefetch(): nothing has been uploaded")
+        self.pending = None
         self.main.wait_event(self.ready[s])
         full = self.d_full[s] if self.world > 1 else self.d_shard[s]
         self.ctx.adopt_csr_device(self.d_indptr[s].data_ptr(), full.data_ptr(), self.n_rows, self.n_cols, self.nnz)

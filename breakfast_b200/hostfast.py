@@ -41,19 +41,33 @@ def _load():
     return _lib
 
 
+_warned = False
+
+
 def available() -> bool:
+    """True when the native host parser can be used.  A missing compiler means "not available" (the Python
+    functions of breakfast.py then do the same work, about three times slower - said once on stderr); a library
+    that was built but does not load or lacks a symbol is a broken installation and raises."""
+    global _warned
     try:
-        _load()
-        return True
-    except Exception:
+        _build.build_host()
+    except RuntimeError as exc:
+        if not _warned:
+            print(f"breakfast_b200: native host parser unavailable ({str(exc).splitlines()[0]}); "
+                  f"using the Python host path", file=sys.stderr)
+            _warned = True
         return False
+    _load()   # OSError / AttributeError propagate: the .so exists but is unusable
+    return True
 
 
 def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length):
-    """meta (DataFrame[id, feature], raw profiles) -> meta_nodups exactly as
-    collapse_duplicates(meta with feature = filter_features(...)) would build it, with the token CSR and the
-    binary CSR of the unique profiles attached in `.attrs["bf_csr"]`.  Returns None when the input cannot
-    take the fast path (a profile containing NUL); the caller then uses the Python functions."""
+    """meta (DataFrame[id, feature], raw profiles) -> (meta_nodups, csr): meta_nodups exactly as
+    collapse_duplicates(meta with feature = filter_features(...)) would build it, csr = the token CSR and the
+    binary CSR of the unique profiles (a plain dict handed to breakfast.cluster(..., pre=csr); it is NOT stored
+    in DataFrame.attrs, which pandas deep-copies on every column access and pickles into the cache).  Returns
+    None when the input cannot take the fast path (a profile containing NUL); the caller then uses the Python
+    functions."""
     from .breakfast import _INVALID, _token_classifier
 
     feats = meta["feature"].tolist()
@@ -118,6 +132,6 @@ def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, tri
     nodups = pd.DataFrame({"id": pd.Series(grouped, dtype=object),
                            "feature": pd.Series(strings, dtype=meta["feature"].dtype)})
     print(f"Number of unique sequences: {n_unique}")
-    nodups.attrs["bf_csr"] = dict(n=n_unique, token_indptr=u_ptr, token_indices=u_idx, n_vocab=int(n_vocab),
-                                  bin_indptr=b_ptr, bin_indices=b_idx, n_cols=int(n_cols))
-    return nodups
+    csr = dict(n=n_unique, token_indptr=u_ptr, token_indices=u_idx, n_vocab=int(n_vocab),
+               bin_indptr=b_ptr, bin_indices=b_idx, n_cols=int(n_cols))
+    return nodups, csr

@@ -230,11 +230,11 @@ def test_native_host_path_equals_python_path(table, opts, capsys):
     capsys.readouterr()
     nd_py, indptr, indices, n_vocab = _python_path(meta, " ", opts)
     out_py = capsys.readouterr().out
-    nd_c = hostfast.prepare(meta, " ", *opts)
+    nd_c, pre = hostfast.prepare(meta, " ", *opts)
     out_c = capsys.readouterr().out
     assert out_c == out_py                                        # same messages in the same order
     assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
-    pre = nd_c.attrs["bf_csr"]
+    assert nd_c.attrs == {}                                       # nothing private rides along in the frame
     assert pre["n_vocab"] == n_vocab
     assert np.array_equal(pre["token_indptr"], indptr) and np.array_equal(pre["token_indices"], indices)
     bi, bx, nc = engine.thermometer_binarise(indptr, indices, n_vocab)
@@ -254,9 +254,9 @@ def test_native_host_path_nextclade_and_multichar_separator(capsys):
                                                            "C300T; G400A", "é1; C300T"]})
     opts = ("nextclade_dna", True, True, 10, 10, 29903)
     nd_py, indptr, indices, n_vocab = _python_path(meta, "; ", opts)
-    nd_c = hostfast.prepare(meta, "; ", *opts)
+    nd_c, pre = hostfast.prepare(meta, "; ", *opts)
     assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
-    assert np.array_equal(nd_c.attrs["bf_csr"]["token_indices"], indices)
+    assert np.array_equal(pre["token_indices"], indices)
 
 
 # ------------------------------------------------------------------ no CPU fallback, no oracle in the product

@@ -58,3 +58,21 @@ def test_cache_max_dist_mismatch_recomputes(tmp_path):
     helpers.run_cli("synthetic/cache_step0.tsv.gz", dict(max_dist=1), tmp_path / "a", cache_out=cache)
     text = helpers.run_cli("synthetic/cache_step1.tsv.gz", dict(max_dist=2), tmp_path / "b", cache_in=cache)
     assert text == (GOLDEN / "synthetic" / "cache_d2_step1_fresh.expected.tsv").read_text()
+
+
+def test_cache_file_carries_no_private_metadata(tmp_path, monkeypatch):
+    """the --output-cache pickle holds {max_dist, version, neigh, meta[id, feature]} and nothing else: the native host
+    path must not leak its CSR arrays into it (the frame's attrs are empty, the file is as small as the Python path's)"""
+    import _pickle
+    import gzip
+    sizes = {}
+    for host in ("native", "python"):
+        monkeypatch.setenv("BREAKFAST_B200_HOST", host)
+        cache = tmp_path / f"cache_{host}"
+        helpers.run_cli("synthetic/cache_step0.tsv.gz", dict(max_dist=1), tmp_path / host, cache_out=cache)
+        with gzip.open(cache, "rb") as fh:
+            payload = _pickle.load(fh)
+        assert sorted(payload) == ["max_dist", "meta", "neigh", "version"]
+        assert payload["meta"].attrs == {} and list(payload["meta"].columns) == ["id", "feature"]
+        sizes[host] = cache.stat().st_size
+    assert abs(sizes["native"] - sizes["python"]) <= 64, sizes
