@@ -52,7 +52,7 @@ _lib = None
 # every symbol include/breakfast_b200.h declares
 EXPORTS = (
     "bf_abi_version", "bf_last_error", "bf_device_count", "bf_ctx_create", "bf_ctx_destroy", "bf_ctx_set_option",
-    "bf_upload_csr", "bf_upload_csr_async", "bf_adopt_csr_device", "bf_run", "bf_labels_to_device", "bf_merge_labels_device", "bf_merge_labels_host",
+    "bf_upload_csr", "bf_upload_csr_async", "bf_csr16_encode", "bf_upload_csr16_async", "bf_adopt_csr_device", "bf_run", "bf_comm_unique_id", "bf_ctx_comm_init_rank", "bf_comm_init_all", "bf_ctx_comm_destroy", "bf_labels_to_device", "bf_merge_labels_device", "bf_merge_labels_host",
     "bf_union_lists", "bf_sync", "bf_download_labels", "bf_edge_count", "bf_download_edges", "bf_cluster_csr",
     "bf_neighbours_csr", "bf_edges_copy", "bf_edges_free", "bf_components", "bf_pinned_alloc", "bf_pinned_free",
     "bf_measure_peak",
@@ -81,8 +81,14 @@ def load() -> C.CDLL:
     lib.bf_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.bf_upload_csr.argtypes = [vp, vp, vp, i64, i32, vp, i64]
     lib.bf_upload_csr_async.argtypes = [vp, vp, vp, i64, i32]
+    lib.bf_csr16_encode.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.bf_upload_csr16_async.argtypes = [vp, vp, vp, vp, i64, i32]
     lib.bf_adopt_csr_device.argtypes = [vp, vp, vp, i64, i32, i64]
     lib.bf_run.argtypes = [vp, i32, i32, i32]
+    lib.bf_comm_unique_id.argtypes = [vp]
+    lib.bf_ctx_comm_init_rank.argtypes = [vp, vp, i32, i32]
+    lib.bf_comm_init_all.argtypes = [C.POINTER(vp), i32]
+    lib.bf_ctx_comm_destroy.argtypes = [vp]
     lib.bf_labels_to_device.argtypes = [vp, vp]
     lib.bf_merge_labels_device.argtypes = [vp, vp, i32]
     lib.bf_merge_labels_host.argtypes = [vp, vp, i32]
@@ -153,6 +159,7 @@ class Context:
         self._h = C.c_void_p()
         _ck(self._lib.bf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.n_rows = 0
+        self.comm = None
         self.set_option("engine", _ENGINES[engine])
         for k, v in options.items():
             self.set_option(k, v)
@@ -196,11 +203,27 @@ class Context:
         self.n_rows = n_rows
         _ck(self._lib.bf_upload_csr_async(self._h, indptr_ptr, indices_ptr, n_rows, int(n_cols)))
 
+    def upload_csr16_async_ptr(self, indptr32_ptr: int, split_ptr: int | None, lo_ptr: int, n_rows: int, n_cols: int):
+        """Compact host form (csr16_encode) from pinned buffers -> idle device slot, decoded on the device."""
+        self.n_rows = n_rows
+        _ck(self._lib.bf_upload_csr16_async(self._h, indptr32_ptr, split_ptr, lo_ptr, n_rows, int(n_cols)))
+
     def adopt_csr_device(self, indptr_dev: int, indices_dev: int, n_rows: int, n_cols: int, nnz: int):
         """Use caller-owned device memory as the CSR (no copy)."""
         self.n_rows = n_rows
         _ck(self._lib.bf_adopt_csr_device(self._h, C.c_void_p(indptr_dev), C.c_void_p(indices_dev), n_rows,
                                           int(n_cols), int(nnz)))
+
+    def comm_init_rank(self, unique_id: bytes, rank: int, world: int):
+        """Join the library's own NCCL communicator (multi-process jobs: one context per process)."""
+        if len(unique_id) != 128:
+            raise ValueError("the communicator id has 128 bytes (comm_unique_id())")
+        _ck(self._lib.bf_ctx_comm_init_rank(self._h, C.c_char_p(unique_id), int(rank), int(world)))
+        self.comm = (int(rank), int(world))
+
+    def comm_destroy(self):
+        _ck(self._lib.bf_ctx_comm_destroy(self._h))
+        self.comm = None
 
     def run(self, max_dist: int, rank: int = 0, world: int = 1):
         _ck(self._lib.bf_run(self._h, int(max_dist), int(rank), int(world)))
@@ -252,6 +275,34 @@ class Context:
         dst = np.empty(n.value, dtype=np.int32)
         _ck(self._lib.bf_download_edges(self._h, _ptr(src), _ptr(dst)))
         return src, dst
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes that identify a new NCCL communicator; rank 0 creates them, every rank passes them to comm_init_rank."""
+    buf = C.create_string_buffer(128)
+    _ck(load().bf_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_all(contexts) -> None:
+    """One process, one Context per distinct device: rank i = contexts[i] (ncclCommInitAll inside the library)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _ck(load().bf_comm_init_all(arr, len(contexts)))
+    for i, c in enumerate(contexts):
+        c.comm = (i, len(contexts))
+
+
+def csr16_encode(indptr, indices, n_cols: int, out=None):
+    """Plain CSR -> compact host form (indptr32 uint32[n+1], split uint16[n] or None, lo uint16[nnz]).  `out` may hold
+    three preallocated arrays (e.g. views of pinned memory).  Raises NativeError(BF_ERR_INVALID) when the matrix is not
+    representable (n_cols > 131072, a row longer than 65535, nnz >= 2^32)."""
+    indptr, indices = _csr_args(indptr, indices)
+    n = indptr.size - 1
+    if out is None:
+        out = (np.empty(n + 1, np.uint32), np.empty(n, np.uint16) if n_cols > 65536 else None, np.empty(indices.size, np.uint16))
+    ip32, split, lo = out
+    _ck(load().bf_csr16_encode(_ptr(indptr), _ptr(indices), n, int(n_cols), _ptr(ip32), _ptr(split), _ptr(lo)))
+    return ip32, split, lo
 
 
 def cluster_csr(indptr, indices, n_cols: int, max_dist: int, device: int = 0, engine="sketch"):

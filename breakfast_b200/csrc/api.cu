@@ -2,13 +2,65 @@
 // Owns device memory, the stream, kernel launches and timers.  No torch, no CPU fallback.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/breakfast_b200.h"
 #include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time: the library does not link libnccl, so it loads (and the single-GPU path works) on a box
+// without it; the first communicator call dlopen()s libnccl.so.2 - the copy already in the process if the caller
+// (torch, say) brought one, else the system's.  Only the handful of entry points the exchange steps need.
+// ------------------------------------------------------------------------------------------------
+namespace bfnccl {
+typedef struct ncclComm* comm_t;
+struct unique_id { char internal[128]; };
+enum { kUint8 = 1 };
+struct Api {
+    int (*GetUniqueId)(unique_id*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+    int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string error;
+    bool ok = false;
+};
+inline Api& api() {
+    static Api a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    const char* names[] = {getenv("BREAKFAST_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names)
+        if (nm && *nm && (h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!h) {
+        a.error = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found");
+        return a;
+    }
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllGather && a.GroupStart && a.GroupEnd && a.GetErrorString;
+    if (!a.ok) a.error = "libnccl.so.2 lacks an expected symbol";
+    return a;
+}
+}  // namespace bfnccl
 
 namespace {
 
@@ -40,6 +92,17 @@ int cuda_fail(cudaError_t e, const char* what, int line) {
     do {                             \
         int rc_ = (expr);            \
         if (rc_ != BF_OK) return rc_; \
+    } while (0)
+
+#define NCK(call)                                                                                   \
+    do {                                                                                            \
+        int r_ = (call);                                                                            \
+        if (r_ != 0) {                                                                              \
+            char buf_[400];                                                                         \
+            snprintf(buf_, sizeof buf_, "NCCL error %d (%s) at api.cu:%d: %s", r_,                  \
+                     bfnccl::api().GetErrorString ? bfnccl::api().GetErrorString(r_) : "?", __LINE__, #call); \
+            return fail(BF_ERR_CUDA, buf_);                                                         \
+        }                                                                                           \
     } while (0)
 
 struct DevBuf {
@@ -97,6 +160,13 @@ struct bf_ctx {
     int64_t items_capacity = 0;  // 0 = auto
     int64_t units_capacity = 0;  // 0 = auto (level-2 queue)
 
+    // communicator of a multi-GPU job (NCCL); with it bf_run does its own exchange steps
+    bfnccl::comm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    int64_t merge_capacity = 0;   // entries per rank of the compact label exchange, 0 = automatic
+    unsigned long long merge_cap_used = 0;
+    DevBuf xchg;
+
     // problem
     bool uploaded = false, ran = false, has_query = false;
     int64_t n_rows = 0, n_query = 0, nnz = 0;
@@ -115,6 +185,7 @@ struct bf_ctx {
     // CSR on the device: two owned slots (async uploads fill the idle one while a pass runs on the
     // other) or caller-owned memory (bf_adopt_csr_device); d_indptr/d_indices is what kernels read
     DevBuf indptr[2], indices[2], query_rows, is_query;
+    DevBuf c16_indptr[2], c16_split[2], c16_lo[2];   // staging of the compact host form, one set per slot
     const int64_t* d_indptr = nullptr;
     const int32_t* d_indices = nullptr;
     int cur = 0, pending = -1;
@@ -123,7 +194,9 @@ struct bf_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
-    DevBuf keysB[2], valsB[2], keysA[2], valsA[2], sort_counts, sort_max, sk_rows;
+    DevBuf keysB[3], valsB[3], keysA[3], valsA[3], sort_counts, sort_max, sk_rows, sched_table;
+    int sort_slots = bf::SORT_MAX_SLOTS;   // radix pass slots launched per sort; lowered to what the data needs after a sync
+    int sched_table_dist = -1, sched_table_n = 0;
     DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, segcnt, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
@@ -143,45 +216,69 @@ int set_device(bf_ctx* c) {
     return BF_OK;
 }
 
-// rows sorted by (clamped) cardinality: keys[0]/vals[0] hold the result (two ping-pong passes)
-// Stable LSD radix sort of (key, row) by the 32-bit composite key (kernels.cuh, K2): four 8-bit passes, of which
-// those whose digit is zero in every key degenerate to a copy (decided on the device from the OR of the keys).
+// Stable LSD radix sort of (key, row) by the 64-bit key c << 32 | s << 16 | t (kernels.cuh, K2) over the bits that
+// occur in the data, eight per pass; keys[0] / vals[0] hold the result whatever the number of passes (three buffers).
 // keys_ready: keys[0] / vals[0] and the OR word of `side` were already written (k_pack_sketch_rows, k_gather_keys).
-int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[2], DevBuf vals[2], int side, bool keys_ready) {
+int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[3], DevBuf vals[3], int side, bool keys_ready) {
     if (n == 0) return BF_OK;
     const int nblocks = (int)ceil_div(n, SORT_ITEMS);
     TRY(c->sort_counts.ensure((size_t)256 * (nblocks + 1) * sizeof(uint32_t)));
-    uint32_t* or_key = c->sort_max.as<uint32_t>() + side;
+    sortkey_t* or_key = c->sort_max.as<sortkey_t>() + side;
     if (!keys_ready) {
-        CK(cudaMemsetAsync(or_key, 0, sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(or_key, 0, sizeof(sortkey_t), c->stream));
         k_card_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_indptr, rows_dev, n,
-                                                              keys[0].as<uint32_t>(), vals[0].as<int32_t>(), or_key);
+                                                              keys[0].as<sortkey_t>(), vals[0].as<int32_t>(), or_key);
         CKLC(c);
     }
-    for (int pass = 0; pass < 4; ++pass) {
-        const int in = pass & 1, out = in ^ 1, shift = 8 * pass;
-        k_sort_hist<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), n, shift,
-                                                    c->sort_counts.as<uint32_t>(), nblocks, or_key);
+    SortBufs b;
+    for (int i = 0; i < 3; ++i) {
+        b.k[i] = keys[i].as<sortkey_t>();
+        b.v[i] = vals[i].as<int32_t>();
+    }
+    unsigned int* needed = &c->counters.as<DevCounters>()->sort_passes;
+    uint32_t* totals = c->sort_counts.as<uint32_t>() + (size_t)256 * nblocks;
+    for (int pass = 0; pass < c->sort_slots; ++pass) {
+        k_sort_hist<<<nblocks, 256, 0, c->stream>>>(b, n, pass, c->sort_counts.as<uint32_t>(), nblocks, or_key, needed);
         CKLC(c);
-        uint32_t* totals = c->sort_counts.as<uint32_t>() + (size_t)256 * nblocks;
-        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, shift, or_key);
+        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, pass, or_key);
         CKLC(c);
-        k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(keys[in].as<uint32_t>(), vals[in].as<int32_t>(), n, shift,
-                                                       c->sort_counts.as<uint32_t>(), totals, nblocks,
-                                                       keys[out].as<uint32_t>(), vals[out].as<int32_t>(), or_key);
+        k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(b, n, pass, c->sort_counts.as<uint32_t>(), totals, nblocks, or_key);
         CKLC(c);
     }
     return BF_OK;
 }
 
-int ensure_sort_buffers(bf_ctx* c, int64_t n, DevBuf keys[2], DevBuf vals[2]) {
-    for (int i = 0; i < 2; ++i) {
-        TRY(keys[i].ensure(std::max<int64_t>(n, 1) * sizeof(uint32_t)));
+int ensure_sort_buffers(bf_ctx* c, int64_t n, DevBuf keys[3], DevBuf vals[3]) {
+    for (int i = 0; i < 3; ++i) {
+        TRY(keys[i].ensure(std::max<int64_t>(n, 1) * sizeof(sortkey_t)));
         TRY(vals[i].ensure(std::max<int64_t>(n, 1) * sizeof(int32_t)));
     }
-    TRY(c->sort_max.ensure(2 * sizeof(uint32_t)));
+    TRY(c->sort_max.ensure(2 * sizeof(sortkey_t)));
     return BF_OK;
 }
+
+// (D, Ds) combinations a partner at distance <= d can have, in ascending order, each with the feasible interval of Dt
+// (kernels.cuh K2b): exists u with |u| + |Ds - u| + |Dt - u| + |D - Ds - Dt + u| <= d
+std::vector<SchedRange> make_sched_table(int d) {
+    std::vector<SchedRange> t;
+    for (int D = -d; D <= d; ++D)
+        for (int Ds = -((d - D) / 2); Ds <= (D + d) / 2; ++Ds) {
+            int lo = 1, hi = 0;
+            for (int Dt = -d; Dt <= d; ++Dt) {
+                bool ok = false;
+                for (int u = -d; u <= d && !ok; ++u)
+                    ok = std::abs(u) + std::abs(Ds - u) + std::abs(Dt - u) + std::abs(D - Ds - Dt + u) <= d;
+                if (ok) {
+                    if (lo > hi) lo = Dt;
+                    hi = Dt;
+                }
+            }
+            if (lo <= hi) t.push_back(SchedRange{(int8_t)D, (int8_t)Ds, (int8_t)lo, (int8_t)hi});
+        }
+    return t;
+}
+
+constexpr int kThreeKeyMaxDist = 8;   // beyond this the (D, Ds) table grows quadratically: two keys
 
 // 128/256-bit sketches (kernels.cuh K1): do the rows of a side go through the staged two-step pack?
 inline bool staged_pack(const bf_ctx* c) {
@@ -190,23 +287,80 @@ inline bool staged_pack(const bf_ctx* c) {
 
 // step 1 of the staged pack: sketches + sort keys of ALL rows of the matrix in storage order (the B side is the
 // whole matrix; a query subset reads its rows' sketches and keys from the same staging arrays)
+// rows the staging arrays must hold: with a communicator every rank owns an equal, block-aligned share (the last ones
+// possibly past the end), so that the shares can be all-gathered in place
+inline bool dist_run(const bf_ctx* c) { return c->comm != nullptr && c->world > 1; }
+inline int64_t staged_rows(const bf_ctx* c) {
+    const int64_t blocks = ceil_div(c->n_rows, TILE);
+    return dist_run(c) ? ceil_div(blocks, c->world) * c->world * TILE : blocks * TILE;
+}
+
 int pack_stage_all_rows(bf_ctx* c) {
     const int64_t n = c->n_rows;
     if (n == 0) return BF_OK;
     int log2m = 0;
     while ((1 << log2m) < c->sketch_bits) ++log2m;
     const int words = c->sketch_bits / 32;
-    TRY(c->sk_rows.ensure((size_t)n * words * sizeof(uint32_t)));
-    uint32_t* or_key = c->sort_max.as<uint32_t>();
-    CK(cudaMemsetAsync(or_key, 0, 2 * sizeof(uint32_t), c->stream));
-    const unsigned blocks = (unsigned)ceil_div(n, TILE);
-    if (words == 4)
-        k_pack_sketch_rows<4><<<blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
-                                                            c->keysB[0].as<uint32_t>(), c->valsB[0].as<int32_t>(), or_key);
-    else
-        k_pack_sketch_rows<8><<<blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
-                                                            c->keysB[0].as<uint32_t>(), c->valsB[0].as<int32_t>(), or_key);
+    TRY(c->sk_rows.ensure((size_t)staged_rows(c) * words * sizeof(uint32_t)));
+    sortkey_t* or_key = c->sort_max.as<sortkey_t>();
+    CK(cudaMemsetAsync(or_key, 0, 2 * sizeof(sortkey_t), c->stream));
+    const int64_t blocks = ceil_div(n, TILE);
+    int64_t block0 = 0, my_blocks = blocks, share = blocks;
+    if (dist_run(c)) {   // this rank streams only its share of the rows; the shares are exchanged below
+        share = ceil_div(blocks, c->world);
+        block0 = share * c->rank;
+        my_blocks = std::max<int64_t>(0, std::min(share, blocks - block0));
+    }
+    if (my_blocks > 0) {
+        if (words == 4)
+            k_pack_sketch_rows<4><<<(unsigned)my_blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
+                                                                             c->keysB[0].as<sortkey_t>(), c->valsB[0].as<int32_t>(), or_key, block0);
+        else
+            k_pack_sketch_rows<8><<<(unsigned)my_blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
+                                                                             c->keysB[0].as<sortkey_t>(), c->valsB[0].as<int32_t>(), or_key, block0);
+        CKLC(c);
+    }
+    if (dist_run(c)) {
+        // exchange step 1: all-gather of the sketch and key shares (16 + 8 bytes per row at 128 bits) over NVLink,
+        // in place; then row numbers and the OR word over all keys
+        bfnccl::Api& nc = bfnccl::api();
+        const size_t rows_share = (size_t)share * TILE;
+        const size_t sk_bytes = rows_share * words * sizeof(uint32_t), key_bytes = rows_share * sizeof(sortkey_t);
+        char* sk = c->sk_rows.as<char>();
+        char* keys = c->keysB[0].as<char>();
+        NCK(nc.GroupStart());
+        NCK(nc.AllGather(sk + (size_t)c->rank * sk_bytes, sk, sk_bytes, bfnccl::kUint8, c->comm, c->stream));
+        NCK(nc.AllGather(keys + (size_t)c->rank * key_bytes, keys, key_bytes, bfnccl::kUint8, c->comm, c->stream));
+        NCK(nc.GroupEnd());
+        CK(cudaMemsetAsync(or_key, 0, sizeof(sortkey_t), c->stream));
+        k_keys_finalize<<<grid_for(n, 256), 256, 0, c->stream>>>(c->keysB[0].as<sortkey_t>(), n, c->valsB[0].as<int32_t>(), or_key);
+        CKLC(c);
+    }
+    return BF_OK;
+}
+
+// exchange step 2 (after verify + hook): every rank publishes the rows of its union-find that are not their own root
+// as (row, root) pairs, the lists are all-gathered and re-united on every rank -> identical forests everywhere
+int exchange_labels(bf_ctx* c) {
+    const int64_t n = c->n_rows;
+    if (n == 0) return BF_OK;
+    bfnccl::Api& nc = bfnccl::api();
+    const unsigned long long cap = c->merge_capacity > 0 ? (unsigned long long)c->merge_capacity
+                                                         : (unsigned long long)std::max<int64_t>(4096, n / 8);
+    c->merge_cap_used = cap;
+    const size_t words_rank = (size_t)cap + 1;
+    TRY(c->xchg.ensure(words_rank * c->world * sizeof(unsigned long long)));
+    unsigned long long* mine = c->xchg.as<unsigned long long>() + words_rank * c->rank;
+    CK(cudaEventRecord(c->ev_aux[0], c->stream));
+    CK(cudaMemsetAsync(mine, 0, sizeof(unsigned long long), c->stream));
+    k_uf_compact<<<grid_for(n, 256), 256, 0, c->stream>>>(c->parent.as<int>(), n, mine, cap);
     CKLC(c);
+    NCK(nc.AllGather(mine, c->xchg.p, words_rank * sizeof(unsigned long long), bfnccl::kUint8, c->comm, c->stream));
+    k_uf_merge_pairs<<<grid_for((int64_t)cap * c->world, 256), 256, 0, c->stream>>>(
+        c->parent.as<int>(), c->xchg.as<unsigned long long>(), c->world, cap, &c->counters.as<DevCounters>()->merge_fullest);
+    CKLC(c);
+    CK(cudaEventRecord(c->ev_aux[1], c->stream));
+    c->ms_merge = -1.f;  // resolved in bf_sync
     return BF_OK;
 }
 
@@ -425,9 +579,14 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query, &c->keysB[0], &c->keysB[1],
-                      &c->valsB[0], &c->valsB[1], &c->keysA[0], &c->keysA[1], &c->valsA[0], &c->valsA[1],
-                      &c->sort_counts, &c->sort_max, &c->sk_rows, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
+    if (c->comm) {
+        bfnccl::api().CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query,
+                      &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->keysB[0], &c->keysB[1], &c->keysB[2],
+                      &c->valsB[0], &c->valsB[1], &c->valsB[2], &c->keysA[0], &c->keysA[1], &c->keysA[2], &c->valsA[0], &c->valsA[1], &c->valsA[2], &c->sched_table,
+                      &c->sort_counts, &c->sort_max, &c->sk_rows, &c->xchg, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -464,6 +623,9 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "level1") {
         if (value != 0 && value != 1) return fail(BF_ERR_INVALID, "level1 must be 0 (integer pipes) or 1 (tensor cores)");
         c->level1 = (int)value;
+    } else if (k == "merge_capacity") {
+        if (value < 0) return fail(BF_ERR_INVALID, "merge_capacity must be >= 0");
+        c->merge_capacity = value;
     } else if (k == "units_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "units_capacity must be >= 0");
         c->units_capacity = value;
@@ -569,6 +731,79 @@ int bf_upload_csr_async(bf_ctx* c, const int64_t* indptr, const int32_t* indices
     return BF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// compact host form ("CSR16")
+// ------------------------------------------------------------------------------------------------
+int bf_csr16_encode(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols, uint32_t* indptr32_out,
+                    uint16_t* split_out, uint16_t* lo_out) {
+    if (n_rows < 0 || n_cols < 0) return fail(BF_ERR_INVALID, "negative size");
+    if (n_cols > 131072) return fail(BF_ERR_INVALID, "CSR16 needs n_cols <= 131072");
+    if (n_rows > 0 && (!indptr || !indptr32_out)) return fail(BF_ERR_INVALID, "null argument");
+    if (n_rows == 0) {
+        if (indptr32_out) indptr32_out[0] = 0;
+        return BF_OK;
+    }
+    const int64_t nnz = indptr[n_rows];
+    if (indptr[0] != 0 || nnz < 0 || nnz > (int64_t)0xffffffffll) return fail(BF_ERR_INVALID, "CSR16 needs 0 <= nnz < 2^32 and indptr[0] == 0");
+    if (nnz > 0 && (!indices || !lo_out)) return fail(BF_ERR_INVALID, "null argument");
+    if (n_cols > 65536 && !split_out) return fail(BF_ERR_INVALID, "split_out is needed when n_cols > 65536");
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        if (e < b) return fail(BF_ERR_INVALID, "indptr must be non-decreasing");
+        if (e - b > 65535) return fail(BF_ERR_INVALID, "CSR16 needs rows of at most 65535 columns");
+        indptr32_out[r] = (uint32_t)b;
+        uint32_t low = 0;
+        for (int64_t k = b; k < e; ++k) {
+            const uint32_t col = (uint32_t)indices[k];
+            if (col >= (uint32_t)n_cols) return fail(BF_ERR_INVALID, "column index out of range");
+            if (k > b && indices[k] <= indices[k - 1]) return fail(BF_ERR_INVALID, "columns of a row must be ascending and unique");
+            low += col < 65536u ? 1u : 0u;
+            lo_out[k] = (uint16_t)(col & 0xffffu);
+        }
+        if (split_out) split_out[r] = (uint16_t)low;
+    }
+    indptr32_out[n_rows] = (uint32_t)nnz;
+    return BF_OK;
+}
+
+int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* split, const uint16_t* lo, int64_t n_rows,
+                          int32_t n_cols) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (n_rows <= 0 || n_cols < 0 || n_cols > 131072 || n_rows > (int64_t)2147483647 - 2 * TILE) return fail(BF_ERR_INVALID, "n_rows/n_cols out of range for CSR16");
+    if (!indptr32) return fail(BF_ERR_INVALID, "indptr32 is null");
+    if (indptr32[0] != 0) return fail(BF_ERR_INVALID, "indptr32[0] must be 0");
+    for (int64_t i = 0; i < n_rows; ++i)
+        if (indptr32[i + 1] < indptr32[i]) return fail(BF_ERR_INVALID, "indptr32 must be non-decreasing");
+    const int64_t nnz = indptr32[n_rows];
+    if (nnz > 0 && !lo) return fail(BF_ERR_INVALID, "lo is null");
+    if (n_cols > 65536 && !split) return fail(BF_ERR_INVALID, "split is needed when n_cols > 65536");
+    TRY(set_device(c));
+    if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is already pending; call bf_run first");
+    const int slot = (c->d_indptr == c->indptr[c->cur].as<int64_t>() && c->d_indptr) ? c->cur ^ 1 : c->cur;
+    TRY(c->indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
+    TRY(c->indices[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    TRY(c->c16_indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(uint32_t)));
+    TRY(c->c16_lo[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(uint16_t)));
+    if (split) TRY(c->c16_split[slot].ensure((size_t)n_rows * sizeof(uint16_t)));
+    if (c->slot_used[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_free[slot], 0));
+    CK(cudaEventRecord(c->ev_upload_start, c->copy_stream));
+    CK(cudaMemcpyAsync(c->c16_indptr[slot].p, indptr32, (size_t)(n_rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (split) CK(cudaMemcpyAsync(c->c16_split[slot].p, split, (size_t)n_rows * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (nnz > 0) CK(cudaMemcpyAsync(c->c16_lo[slot].p, lo, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+    // decode on the copy stream as well: it overlaps the pass that is still running on the other slot
+    k_csr16_decode<<<c->num_sms * 8, 256, 0, c->copy_stream>>>(c->c16_indptr[slot].as<uint32_t>(), split ? c->c16_split[slot].as<uint16_t>() : nullptr,
+                                                               c->c16_lo[slot].as<uint16_t>(), n_rows, c->indptr[slot].as<int64_t>(),
+                                                               c->indices[slot].as<int32_t>());
+    CKLC(c);
+    CK(cudaEventRecord(c->ev_upload_done, c->copy_stream));
+    c->pending = slot;
+    c->pend_rows = n_rows;
+    c->pend_cols = n_cols;
+    c->pend_nnz = nnz;
+    c->uploaded = true;
+    return BF_OK;
+}
+
 int bf_adopt_csr_device(bf_ctx* c, const void* indptr_device, const void* indices_device, int64_t n_rows,
                         int32_t n_cols, int64_t nnz) {
     if (!c) return fail(BF_ERR_INVALID, "ctx is null");
@@ -592,6 +827,9 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     if (!c->uploaded) return fail(BF_ERR_STATE, "bf_run before bf_upload_csr");
     if (max_dist < 0) return fail(BF_ERR_INVALID, "max_dist must be >= 0");
     if (world < 1 || rank < 0 || rank >= world) return fail(BF_ERR_INVALID, "need 0 <= rank < world");
+    if (c->comm && world > 1 && (rank != c->comm_rank || world != c->comm_world))
+        return fail(BF_ERR_INVALID, "rank/world differ from the communicator of this context");
+    if (c->comm && world > 1 && !bfnccl::api().ok) return fail(BF_ERR_STATE, bfnccl::api().error);
     TRY(set_device(c));
     if (c->pending >= 0) {
         // the CSR of this pass was uploaded asynchronously into the idle slot: order after the copy
@@ -645,15 +883,15 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     DevBuf* valsA = c->has_query ? c->valsA : c->valsB;
     if (active) {
         // ---- K2: sort keys (+ the staged sketches, which come out of the same pass over the columns) and sort
-        TRY(ensure_sort_buffers(c, nB, c->keysB, c->valsB));
+        TRY(ensure_sort_buffers(c, std::max(nB, staged_pack(c) ? staged_rows(c) : nB), c->keysB, c->valsB));
         if (c->has_query) TRY(ensure_sort_buffers(c, nA, c->keysA, c->valsA));
         const bool staged = staged_pack(c);
         if (staged) {
             TRY(pack_stage_all_rows(c));
             if (c->has_query) {   // before the sort of the B side reuses keysB[0]
-                k_gather_keys<<<grid_for(nA, 256), 256, 0, c->stream>>>(c->keysB[0].as<uint32_t>(), c->query_rows.as<int32_t>(), nA,
-                                                                        c->keysA[0].as<uint32_t>(), c->valsA[0].as<int32_t>(),
-                                                                        c->sort_max.as<uint32_t>() + 1);
+                k_gather_keys<<<grid_for(nA, 256), 256, 0, c->stream>>>(c->keysB[0].as<sortkey_t>(), c->query_rows.as<int32_t>(), nA,
+                                                                        c->keysA[0].as<sortkey_t>(), c->valsA[0].as<int32_t>(),
+                                                                        c->sort_max.as<sortkey_t>() + 1);
                 CKLC(c);
             }
         }
@@ -669,7 +907,17 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(c->ev[2], c->stream));
     if (active) {
         // ---- K2b: schedule
-        const int n_ranges = 2 * max_dist + 1;
+        // three sort keys where the sketch pass produced them and the (D, Ds) table stays small, else the plain band
+        const int n_keys = staged_pack(c) ? (max_dist <= kThreeKeyMaxDist ? 3 : 2) : 1;
+        if (n_keys == 3 && c->sched_table_dist != max_dist) {
+            const std::vector<SchedRange> table = make_sched_table(max_dist);
+            TRY(c->sched_table.ensure(std::max<size_t>(table.size(), 1) * sizeof(SchedRange)));
+            CK(cudaMemcpyAsync(c->sched_table.p, table.data(), table.size() * sizeof(SchedRange), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));   // `table` is pageable and goes out of scope (once per max_dist)
+            c->sched_table_dist = max_dist;
+            c->sched_table_n = (int)table.size();
+        }
+        const int n_ranges = n_keys == 3 ? std::max(c->sched_table_n, 2 * max_dist + 1) : (n_keys == 2 ? 2 * max_dist + 1 : 1);
         const int64_t n_entries = c->tilesA * n_ranges;
         c->sched_ranges = n_ranges;
         TRY(c->jlo.ensure((size_t)n_entries * sizeof(int32_t)));
@@ -677,7 +925,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         TRY(c->jend.ensure((size_t)n_entries * sizeof(int32_t)));
         const int group = c->ran_two_kernel ? L1_GROUP : 1;
         k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
-            keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, c->has_query ? 0 : 1, group,
+            keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, c->has_query ? 0 : 1, group, n_keys, n_ranges,
+            c->sched_table.as<SchedRange>(), n_keys == 3 ? c->sched_table_n : 0,
             c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),
             &c->counters.as<DevCounters>()->n_tilepairs);
         CKLC(c);
@@ -685,10 +934,10 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
         CKLC(c);
         DevCounters* dc = c->counters.as<DevCounters>();
-        k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, c->keysB[0].as<uint32_t>(), nB, max_dist, &dc->band_ab);
+        k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, &dc->band_ab);
         CKLC(c);
         if (c->has_query) {
-            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<uint32_t>(), nA, keysA[0].as<uint32_t>(), nA, max_dist, &dc->band_aa);
+            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, keysA[0].as<sortkey_t>(), nA, max_dist, &dc->band_aa);
             CKLC(c);
         }
         // explicit work list for the producer (bounded; items beyond it fall back to a binary search)
@@ -750,6 +999,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         CKLC(c);
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
+    // ---- exchange step 2 (multi-GPU with the library's own communicator): merge the ranks' forests
+    if (dist_run(c)) TRY(exchange_labels(c));
     // ---- K4: labels
     TRY(finish_labels(c));
     CK(cudaEventRecord(c->ev[6], c->stream));
@@ -760,6 +1011,68 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     }
     ++c->runs_since_sync;
     c->ran = true;
+    return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// communicators
+// ------------------------------------------------------------------------------------------------
+int bf_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(BF_ERR_INVALID, "id_out is null");
+    bfnccl::Api& nc = bfnccl::api();
+    if (!nc.ok) return fail(BF_ERR_STATE, nc.error);
+    bfnccl::unique_id id;
+    NCK(nc.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return BF_OK;
+}
+
+int bf_ctx_comm_init_rank(bf_ctx* c, const void* id, int32_t rank, int32_t world) {
+    if (!c || !id) return fail(BF_ERR_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(BF_ERR_INVALID, "need 0 <= rank < world");
+    if (c->comm) return fail(BF_ERR_STATE, "the context already has a communicator");
+    bfnccl::Api& nc = bfnccl::api();
+    if (!nc.ok) return fail(BF_ERR_STATE, nc.error);
+    TRY(set_device(c));
+    bfnccl::unique_id uid;
+    memcpy(&uid, id, sizeof uid);
+    NCK(nc.CommInitRank(&c->comm, world, uid, rank));
+    c->comm_rank = rank;
+    c->comm_world = world;
+    return BF_OK;
+}
+
+int bf_comm_init_all(bf_ctx** ctxs, int32_t n) {
+    if (!ctxs || n < 1 || n > 64) return fail(BF_ERR_INVALID, "need 1 .. 64 contexts");
+    int devs[64];
+    bfnccl::comm_t comms[64];
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) return fail(BF_ERR_INVALID, "null context");
+        if (ctxs[i]->comm) return fail(BF_ERR_STATE, "a context already has a communicator");
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(BF_ERR_INVALID, "NCCL needs one context per distinct device");
+    }
+    bfnccl::Api& nc = bfnccl::api();
+    if (!nc.ok) return fail(BF_ERR_STATE, nc.error);
+    NCK(nc.CommInitAll(comms, n, devs));
+    for (int i = 0; i < n; ++i) {
+        ctxs[i]->comm = comms[i];
+        ctxs[i]->comm_rank = i;
+        ctxs[i]->comm_world = n;
+    }
+    return BF_OK;
+}
+
+int bf_ctx_comm_destroy(bf_ctx* c) {
+    if (!c) return fail(BF_ERR_INVALID, "ctx is null");
+    if (!c->comm) return BF_OK;
+    TRY(set_device(c));
+    CK(cudaStreamSynchronize(c->stream));
+    NCK(bfnccl::api().CommDestroy(c->comm));
+    c->comm = nullptr;
+    c->comm_rank = 0;
+    c->comm_world = 1;
     return BF_OK;
 }
 
@@ -920,6 +1233,18 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
     {
         std::string what;
         char buf[200];
+        if (c->n_query > 0 && c->n_rows > 0 && h.sort_passes > 0) {
+            if ((int)h.sort_passes > c->sort_slots) {
+                snprintf(buf, sizeof buf, "radix sort: %u passes > %d launched; ", h.sort_passes, c->sort_slots);
+                what += buf;
+            }
+            c->sort_slots = std::min<int>(SORT_MAX_SLOTS, (int)h.sort_passes);   // exactly what this data needs from now on
+        }
+        if (dist_run(c) && h.merge_fullest > c->merge_cap_used) {
+            c->merge_capacity = (int64_t)h.merge_fullest + h.merge_fullest / 4 + 1024;
+            snprintf(buf, sizeof buf, "label exchange: %u entries > capacity %llu; ", h.merge_fullest, c->merge_cap_used);
+            what += buf;
+        }
         if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
             if (nwork > c->items_cap_used) {
                 c->items_capacity = (int64_t)(nwork + 1024);

@@ -48,53 +48,107 @@ struct DevCounters {
     unsigned long long n_units;        // level-2 queue cursor (may exceed capacity -> overflow)
     unsigned int n_comp;
     unsigned int seg_max;              // fullest per-CTA segment of the level-2 pair queue (overflow check)
+    unsigned int sort_passes;          // radix pass slots the keys of this run need (max over the sorted sides)
+    unsigned int merge_fullest;        // longest compact label list of any rank in the exchange step (overflow check)
 };
 
 // ------------------------------------------------------------------------------------------
-// K2: sort keys + stable LSD radix sort (up to 4 x 8 bits) — deterministic permutation
+// K2: sort keys + stable LSD radix sort (8-bit digits over the bits that occur) — deterministic permutation
 //
-// key = c << 16 | s with c = |A| (the row's cardinality) and s = |A n H|, H = the columns whose hash has its top
-// bit set (s = 0 for the engines that do not stream the columns before the sort: H = {} is as valid as any H).
-// For two rows, |A xor B| >= |s_A - s_B| + |(c_A - s_A) - (c_B - s_B)|: the two halves of the column space are
-// disjoint.  Sorting by (c, s) therefore turns the partners of a row into at most 2 d + 1 contiguous runs, one
-// per c' = c - d .. c + d, each bounded in s (see k_schedule) - about five times fewer tile pairs than the plain
-// cardinality band on SARS-CoV-2-shaped profiles.  Both halves are clamped to 16 bits; k_schedule drops the s
-// bound wherever a clamped value could be involved, so the band test stays sound for any input.
+// key = c << 32 | s << 16 | t with c = |A| (the row's cardinality), s = |A n H1| and t = |A n H2|, H1 / H2 = the columns
+// whose multiplicative hash has bit 31 / bit 30 set (s = t = 0 for the engines that do not stream the columns before
+// the sort: H = {} is as valid as any H).  H1 and H2 cut the column space into four disjoint quadrants, and
+// |A xor B| >= the sum over the quadrants of | |A n Q| - |B n Q| |.  Sorting by (c, s, t) therefore turns the partners of
+// a row into a few contiguous runs, one per feasible (c' - c, s' - s), each bounded in t (see k_schedule) - about eight
+// times fewer tile pairs than the plain cardinality band on SARS-CoV-2-shaped profiles (two keys: about four times).
+// c is clamped to 16 bits (s, t <= c); k_schedule drops the s / t bounds wherever the clamped group is involved, so the
+// band test stays sound for any input.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sort_key(int64_t card, uint32_t sub) {
-    if (card >= (int64_t)KEY_CLAMP) return KEY_CLAMP << 16;   // clamped group: s carries no information
-    return ((uint32_t)card << 16) | sub;                      // sub <= card < 65535
+typedef unsigned long long sortkey_t;
+
+__device__ __forceinline__ sortkey_t sort_key(int64_t card, uint32_t s, uint32_t t) {
+    if (card >= (int64_t)KEY_CLAMP) return (sortkey_t)KEY_CLAMP << 32;   // clamped group: s and t carry no information
+    return ((sortkey_t)card << 32) | ((sortkey_t)s << 16) | (sortkey_t)t;   // s, t <= card < 65535
+}
+__device__ __forceinline__ uint32_t key_card(sortkey_t k) { return (uint32_t)(k >> 32); }
+
+// OR of all keys -> one atomic per warp; the radix passes run over the set bits of this word only
+__device__ __forceinline__ void or_reduce_key(sortkey_t k, sortkey_t* __restrict__ or_key) {
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)k), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(k >> 32));
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(or_key, ((sortkey_t)hi << 32) | lo);
 }
 
 __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
-                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
-                            uint32_t* __restrict__ or_key) {
+                            int64_t n, sortkey_t* __restrict__ keys, int32_t* __restrict__ vals,
+                            sortkey_t* __restrict__ or_key) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    uint32_t k = 0;
+    sortkey_t k = 0;
     if (q < n) {
         int32_t r = rows ? rows[q] : (int32_t)q;
-        k = sort_key(indptr[r + 1] - indptr[r], 0u);
+        k = sort_key(indptr[r + 1] - indptr[r], 0u, 0u);
         keys[q] = k;
         vals[q] = r;
     }
-    // OR of all keys -> one atomic per warp; a radix pass whose digits are all zero is skipped
-    k = __reduce_or_sync(0xffffffffu, k);
-    if ((threadIdx.x & 31) == 0 && k) atomicOr(or_key, k);
+    or_reduce_key(k, or_key);
 }
 
 // keys of a row subset from the per-row keys of the whole matrix (written by k_pack_sketch_rows)
-__global__ void k_gather_keys(const uint32_t* __restrict__ row_keys, const int32_t* __restrict__ rows, int64_t n,
-                              uint32_t* __restrict__ keys, int32_t* __restrict__ vals, uint32_t* __restrict__ or_key) {
+__global__ void k_gather_keys(const sortkey_t* __restrict__ row_keys, const int32_t* __restrict__ rows, int64_t n,
+                              sortkey_t* __restrict__ keys, int32_t* __restrict__ vals, sortkey_t* __restrict__ or_key) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    uint32_t k = 0;
+    sortkey_t k = 0;
     if (q < n) {
         const int32_t r = rows[q];
         k = row_keys[r];
         keys[q] = k;
         vals[q] = r;
     }
-    k = __reduce_or_sync(0xffffffffu, k);
-    if ((threadIdx.x & 31) == 0 && k) atomicOr(or_key, k);
+    or_reduce_key(k, or_key);
+}
+
+// The sort runs over the COMPRESSED key: the bits that are set in at least one key (or_key), eight per pass, so real
+// data (cardinalities below 256, half cardinalities below 128: about 22 bits) needs three passes instead of six.
+// The host launches `slots` pass slots; slot p is real pass p if p < R = ceil(popc(or_key) / 8) and returns at once
+// otherwise (the host learns R at the next bf_sync and launches exactly R slots from then on; too few slots are an
+// overflow like any other and the pass is run again).  Three buffers make the result land in buffer 0 for any R:
+//   R even: 0 -> 1 -> 0 ...      R odd >= 3: 0 -> 2 -> 1 -> 0 -> 1 -> 0 ...      R = 1: 0 -> 1, slot 1 copies 1 -> 0.
+struct SortBufs {
+    sortkey_t* k[3];
+    int32_t* v[3];
+};
+struct SortPlan {
+    bool active, copy_only;
+    int in, out;
+    uint32_t pos[8];   // bit positions of this pass's digit bits (unused ones point at bit 63, which no key has)
+};
+__device__ __forceinline__ int sort_passes_needed(sortkey_t or_key) {
+    const int R = (__popcll(or_key) + 7) >> 3;
+    return R == 1 ? 2 : R;
+}
+__device__ __forceinline__ SortPlan sort_plan(sortkey_t or_key, int p) {
+    SortPlan pl;
+    const int R = (__popcll(or_key) + 7) >> 3;
+    pl.active = p < R || (R == 1 && p == 1);
+    pl.copy_only = R == 1 && p == 1;
+    if ((R & 1) == 0) { pl.in = p & 1; pl.out = pl.in ^ 1; }
+    else if (R == 1) { pl.in = p; pl.out = p ^ 1; }
+    else if (p == 0) { pl.in = 0; pl.out = 2; }
+    else if (p == 1) { pl.in = 2; pl.out = 1; }
+    else { pl.in = (p + 1) & 1; pl.out = pl.in ^ 1; }
+    sortkey_t m = or_key;
+    for (int i = 0; i < 8 * p && m; ++i) m &= m - 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pl.pos[i] = m ? (uint32_t)(__ffsll((long long)m) - 1) : 63u;
+        m &= m - 1;
+    }
+    return pl;
+}
+__device__ __forceinline__ uint32_t sort_digit(sortkey_t key, const uint32_t (&pos)[8]) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d |= (uint32_t)((key >> pos[i]) & 1ull) << i;
+    return d;
 }
 
 // One radix pass = k_sort_hist -> k_sort_scan_digits -> k_sort_scatter.  A block owns SORT_ITEMS
@@ -104,28 +158,31 @@ __global__ void k_gather_keys(const uint32_t* __restrict__ row_keys, const int32
 // counts[digit * nblocks + block] = number of rows of `block` whose digit == digit
 constexpr int SORT_WARPS = 8;
 constexpr int SORT_PER_WARP = SORT_ITEMS / SORT_WARPS;
+constexpr int SORT_MAX_SLOTS = 6;   // 48 key bits
 
-__device__ __forceinline__ void sort_warp_count(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t wbase,
+__device__ __forceinline__ void sort_warp_count(const sortkey_t* __restrict__ keys, int64_t n, const uint32_t (&pos)[8], int64_t wbase,
                                                 uint32_t* __restrict__ whist, int lane) {
     for (int r = 0; r < SORT_PER_WARP; r += 32) {
         const int64_t i = wbase + r + lane;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;  // invalid lanes match nobody
+        const uint32_t d = valid ? sort_digit(keys[i], pos) : 256u + lane;  // invalid lanes match nobody
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[d] += __popc(peers);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
-                                                   uint32_t* __restrict__ counts, int nblocks,
-                                                   const uint32_t* __restrict__ or_key) {
-    if (((*or_key >> shift) & 255u) == 0) return;  // every digit of this pass is 0: identity pass
+__global__ void __launch_bounds__(256) k_sort_hist(SortBufs b, int64_t n, int p, uint32_t* __restrict__ counts, int nblocks,
+                                                   const sortkey_t* __restrict__ or_key, unsigned int* __restrict__ passes_needed) {
+    const sortkey_t ok = *or_key;
+    if (p == 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(passes_needed, (unsigned int)sort_passes_needed(ok));
+    const SortPlan pl = sort_plan(ok, p);
+    if (!pl.active || pl.copy_only) return;
     __shared__ uint32_t whist[SORT_WARPS][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
     __syncthreads();
-    sort_warp_count(keys, n, shift, (int64_t)blockIdx.x * SORT_ITEMS + warp * SORT_PER_WARP, whist[warp], lane);
+    sort_warp_count(b.k[pl.in], n, pl.pos, (int64_t)blockIdx.x * SORT_ITEMS + warp * SORT_PER_WARP, whist[warp], lane);
     __syncthreads();
     uint32_t c = 0;
 #pragma unroll
@@ -137,9 +194,10 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ 
 // over the blocks (in place) and leaves the digit's total in totals[digit]; k_sort_scatter adds the exclusive
 // scan over the 256 digit totals itself.
 __global__ void __launch_bounds__(256) k_sort_scan_digits(uint32_t* __restrict__ counts, int nblocks,
-                                                          uint32_t* __restrict__ totals, int shift,
-                                                          const uint32_t* __restrict__ or_key) {
-    if (((*or_key >> shift) & 255u) == 0) return;
+                                                          uint32_t* __restrict__ totals, int p,
+                                                          const sortkey_t* __restrict__ or_key) {
+    const int R = (__popcll(*or_key) + 7) >> 3;
+    if (p >= R) return;
     const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint32_t* row = counts + (size_t)d * nblocks;
     uint32_t carry = 0;
@@ -158,15 +216,18 @@ __global__ void __launch_bounds__(256) k_sort_scan_digits(uint32_t* __restrict__
     if (lane == 0) totals[d] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys,
-                                                      const int32_t* __restrict__ vals, int64_t n, int shift,
+__global__ void __launch_bounds__(256) k_sort_scatter(SortBufs b, int64_t n, int p,
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ totals, int nblocks,
-                                                      uint32_t* __restrict__ keys_out,
-                                                      int32_t* __restrict__ vals_out,
-                                                      const uint32_t* __restrict__ or_key) {
+                                                      const sortkey_t* __restrict__ or_key) {
+    const SortPlan pl = sort_plan(*or_key, p);
+    if (!pl.active) return;
+    const sortkey_t* __restrict__ keys = b.k[pl.in];
+    const int32_t* __restrict__ vals = b.v[pl.in];
+    sortkey_t* __restrict__ keys_out = b.k[pl.out];
+    int32_t* __restrict__ vals_out = b.v[pl.out];
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
-    if (((*or_key >> shift) & 255u) == 0) {  // identity pass: plain copy
+    if (pl.copy_only) {  // a single real pass left the result in buffer 1
         const int m = (int)min((int64_t)SORT_ITEMS, n - base);
         for (int i = threadIdx.x; i < m; i += 256) {
             keys_out[base + i] = keys[base + i];
@@ -179,7 +240,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
     __syncthreads();
     const int64_t wbase = base + warp * SORT_PER_WARP;
-    sort_warp_count(keys, n, shift, wbase, whist[warp], lane);
+    sort_warp_count(keys, n, pl.pos, wbase, whist[warp], lane);
     __syncthreads();
     __shared__ uint32_t wsum[SORT_WARPS];
     uint32_t digit_base;   // exclusive scan over the 256 digit totals (thread = digit)
@@ -212,8 +273,8 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     for (int r = 0; r < SORT_PER_WARP; r += 32) {
         const int64_t i = wbase + r + lane;
         const bool valid = i < n;
-        const uint32_t k = valid ? keys[i] : 0u;
-        const uint32_t d = valid ? ((k >> shift) & 255u) : 256u + lane;
+        const sortkey_t k = valid ? keys[i] : 0ull;
+        const uint32_t d = valid ? sort_digit(k, pl.pos) : 256u + lane;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const unsigned below = peers & ((1u << lane) - 1u);
         uint32_t pos = 0;
@@ -283,65 +344,101 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, i
 
 // ------------------------------------------------------------------------------------------
 // K2b: band-pruned tile schedule.  keys are sorted ascending, so a tile's min/max are its ends.
-// Row tile I gets n_ranges = 2 d + 1 schedule entries e = I * n_ranges + r, each one contiguous range
-// [jlo[e], jend[e]) of B tiles:
-//   * all rows of the tile share one (unclamped) cardinality c: entry r covers the partners of cardinality
-//     c' = c - d + r.  With D = c' - c, a partner needs |s' - s| + |D - (s' - s)| <= d, i.e.
-//     s' - s in [-(d - D) / 2, (D + d) / 2] (integer divisions of non-negative numbers), so the entry is the run
-//     c' << 16 | smin - (d - D) / 2  ..  c' << 16 | smax + (D + d) / 2; no s bound against the clamped group;
-//   * otherwise (tile across a cardinality boundary, or clamped rows): entry 0 = the plain cardinality band
+// Row tile I gets n_ranges schedule entries e = I * n_ranges + r, each one contiguous range [jlo[e], jend[e]) of B tiles.
+// With D = c' - c, Ds = s' - s, Dt = t' - t for a partner (c', s', t') of a row (c, s, t) and u = the (unknown)
+// difference on the quadrant H1 n H2, the four quadrant differences are u, Ds - u, Dt - u, D - Ds - Dt + u, so
+//     |A xor B| >= min over u of |u| + |Ds - u| + |Dt - u| + |D - Ds - Dt + u|.
+//   * n_keys = 3 and all rows of the tile share (c, s), c unclamped: one entry per feasible (D, Ds) - the host lists
+//     them in ascending order with the feasible interval [dt_min, dt_max] of Dt (SchedRange table) - covering the keys
+//     (c + D, s + Ds, tmin + dt_min) .. (c + D, s + Ds, tmax + dt_max); no s / t bound against the clamped group;
+//   * else if all rows share one unclamped c (n_keys >= 2): entry per D = -d .. d with
+//     s' - s in [-(d - D) / 2, (D + d) / 2] (integer divisions of non-negative numbers), any t;
+//   * otherwise (tile across a cardinality boundary, clamped rows, n_keys = 1): entry 0 = the plain cardinality band
 //     cmin - d .. cmax + d, the other entries empty.
 // Ranges are clipped so that no B tile is listed twice for a row tile (and to J >= I in the triangular case).
 // ------------------------------------------------------------------------------------------
 // `group` column tiles form one work item (1 for the single-kernel path, L1_GROUP for the two-kernel
 // path); an item never spans two entries; count[I] = number of work items of row tile I (all its entries),
 // *n_tilepairs += number of tile pairs.
-__global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const uint32_t* __restrict__ keysB,
-                           int64_t nB, int max_dist, int triangular, int group, int32_t* __restrict__ jlo,
+struct SchedRange {
+    int8_t D, Ds, dt_min, dt_max;
+};
+
+__global__ void k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __restrict__ keysB,
+                           int64_t nB, int max_dist, int triangular, int group, int n_keys, int n_ranges,
+                           const SchedRange* __restrict__ table3, int n_table3, int32_t* __restrict__ jlo,
                            int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
                            unsigned long long* __restrict__ n_tilepairs) {
     const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
     int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (I >= tA) return;
-    const int n_ranges = 2 * max_dist + 1;
-    const uint32_t kMin = keysA[I * TILE], kMax = keysA[min(nA, (I + 1) * TILE) - 1];
-    const int64_t cMin = kMin >> 16, cMax = kMax >> 16, sMin = kMin & 0xffffu, sMax = kMax & 0xffffu;
-    const bool single = cMin == cMax && cMax < (int64_t)KEY_CLAMP;
+    const sortkey_t kMin = keysA[I * TILE], kMax = keysA[min(nA, (I + 1) * TILE) - 1];
+    const int64_t cMin = (int64_t)(kMin >> 32), cMax = (int64_t)(kMax >> 32);
+    const int64_t sMin = (int64_t)((kMin >> 16) & 0xffffu), sMax = (int64_t)((kMax >> 16) & 0xffffu);
+    const int64_t tMin = (int64_t)(kMin & 0xffffu), tMax = (int64_t)(kMax & 0xffffu);
+    const bool single_c = n_keys >= 2 && cMin == cMax && cMax < (int64_t)KEY_CLAMP;
+    const bool single_cs = n_keys >= 3 && single_c && sMin == sMax;
+    const int n_gen = single_cs ? n_table3 : (single_c ? 2 * max_dist + 1 : 1);
     int64_t prev_end = triangular ? I : 0;
     unsigned long long tp_sum = 0, items_sum = 0;
+    bool clamp_done = false;
     for (int r = 0; r < n_ranges; ++r) {
-        int64_t lo_key = 1, hi_key = 0;   // empty
-        if (single) {
-            const int64_t D = (int64_t)r - max_dist, c2 = cMin + D;
-            if (c2 >= 0 && c2 <= (int64_t)KEY_CLAMP) {
-                int64_t s_lo = 0, s_hi = 0xffff;
-                if (c2 < (int64_t)KEY_CLAMP) {
-                    s_lo = max((int64_t)0, sMin - (max_dist - D) / 2);
-                    s_hi = min((int64_t)0xffff, sMax + (D + max_dist) / 2);
+        bool have = false;
+        sortkey_t lo_key = 0, hi_key = 0;
+        if (r < n_gen) {
+            if (single_cs) {
+                const SchedRange e = table3[r];
+                const int64_t c2 = cMin + e.D, s2 = sMin + e.Ds;
+                if (c2 >= 0 && c2 <= (int64_t)KEY_CLAMP) {
+                    if (c2 == (int64_t)KEY_CLAMP) {   // the clamped group carries no s / t: listed once, as a whole
+                        if (!clamp_done) {
+                            have = clamp_done = true;
+                            lo_key = (sortkey_t)c2 << 32;
+                            hi_key = ((sortkey_t)c2 << 32) | 0xffffffffull;
+                        }
+                    } else if (s2 >= 0) {
+                        const int64_t t_lo = max((int64_t)0, tMin + e.dt_min), t_hi = min((int64_t)0xffff, tMax + e.dt_max);
+                        if (t_lo <= t_hi) {
+                            have = true;
+                            lo_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s2 << 16) | (sortkey_t)t_lo;
+                            hi_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s2 << 16) | (sortkey_t)t_hi;
+                        }
+                    }
                 }
-                lo_key = (c2 << 16) | s_lo;
-                hi_key = (c2 << 16) | s_hi;
+            } else if (single_c) {
+                const int64_t D = (int64_t)r - max_dist, c2 = cMin + D;
+                if (c2 >= 0 && c2 <= (int64_t)KEY_CLAMP) {
+                    int64_t s_lo = 0, s_hi = 0xffff;
+                    if (c2 < (int64_t)KEY_CLAMP) {
+                        s_lo = max((int64_t)0, sMin - (max_dist - D) / 2);
+                        s_hi = min((int64_t)0xffff, sMax + (D + max_dist) / 2);
+                    }
+                    have = true;
+                    lo_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s_lo << 16);
+                    hi_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s_hi << 16) | 0xffffull;
+                }
+            } else {
+                have = true;
+                lo_key = (sortkey_t)max((int64_t)0, cMin - max_dist) << 32;
+                hi_key = ((sortkey_t)min((int64_t)KEY_CLAMP, cMax + max_dist) << 32) | 0xffffffffull;
             }
-        } else if (r == 0) {
-            lo_key = max((int64_t)0, cMin - max_dist) << 16;
-            hi_key = (min((int64_t)KEY_CLAMP, cMax + max_dist) << 16) | 0xffff;
         }
         int64_t first = prev_end, end = prev_end;
-        if (lo_key <= hi_key) {
+        if (have) {
             // first J with bMax[J] >= lo_key
             int64_t l = 0, rr = tB;
             while (l < rr) {
                 const int64_t mid = (l + rr) >> 1;
-                const uint32_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
-                if ((int64_t)bMax >= lo_key) rr = mid; else l = mid + 1;
+                const sortkey_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
+                if (bMax >= lo_key) rr = mid; else l = mid + 1;
             }
             first = l;
             // first J with bMin[J] > hi_key
             l = 0; rr = tB;
             while (l < rr) {
                 const int64_t mid = (l + rr) >> 1;
-                const uint32_t bMin = keysB[mid * TILE];
-                if ((int64_t)bMin > hi_key) rr = mid; else l = mid + 1;
+                const sortkey_t bMin = keysB[mid * TILE];
+                if (bMin > hi_key) rr = mid; else l = mid + 1;
             }
             end = l;
             first = max(first, prev_end);
@@ -362,17 +459,17 @@ __global__ void k_schedule(const uint32_t* __restrict__ keysA, int64_t nA, const
 // ordered in-band count: for every x in X, #{y in Y : ||x| - |y|| <= d}.  The metric's candidate pairs are defined
 // on the cardinalities alone (upper key halves).  X is sorted, so only the first row of every run of equal
 // cardinality searches (three binary searches) and counts for its whole run.
-__global__ void __launch_bounds__(256) k_band_count(const uint32_t* __restrict__ keysX, int64_t nX,
-                                                    const uint32_t* __restrict__ keysY, int64_t nY, int max_dist,
+__global__ void __launch_bounds__(256) k_band_count(const sortkey_t* __restrict__ keysX, int64_t nX,
+                                                    const sortkey_t* __restrict__ keysY, int64_t nY, int max_dist,
                                                     unsigned long long* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned long long c = 0;
     if (i < nX) {
-        const uint32_t k = keysX[i] >> 16;
-        if (i == 0 || (keysX[i - 1] >> 16) != k) {
-            const uint32_t lo_t = (k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u) << 16;
-            const uint32_t hi_t = (min(k + (uint32_t)max_dist, KEY_CLAMP) << 16) | 0xffffu;
-            const uint32_t run_t = (k << 16) | 0xffffu;
+        const uint32_t k = key_card(keysX[i]);
+        if (i == 0 || key_card(keysX[i - 1]) != k) {
+            const sortkey_t lo_t = (sortkey_t)(k > (uint32_t)max_dist ? k - (uint32_t)max_dist : 0u) << 32;
+            const sortkey_t hi_t = ((sortkey_t)min(k + (uint32_t)max_dist, KEY_CLAMP) << 32) | 0xffffffffull;
+            const sortkey_t run_t = ((sortkey_t)k << 32) | 0xffffffffull;
             int64_t l = i, r = nX;   // end of this run in X
             while (l < r) { int64_t m = (l + r) >> 1; if (keysX[m] > run_t) r = m; else l = m + 1; }
             const int64_t run = l - i;
@@ -519,13 +616,15 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
 template <int WORDS>
 __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restrict__ indptr,
                                                           const int32_t* __restrict__ indices, int64_t n, int log2m,
-                                                          uint32_t* __restrict__ sk_rows, uint32_t* __restrict__ keys,
-                                                          int32_t* __restrict__ vals, uint32_t* __restrict__ or_key) {
+                                                          uint32_t* __restrict__ sk_rows, sortkey_t* __restrict__ keys,
+                                                          int32_t* __restrict__ vals, sortkey_t* __restrict__ or_key,
+                                                          int64_t block0) {
+    // block0: first 128-row block of this launch (a rank of a multi-GPU job takes a contiguous share of the blocks)
     __shared__ uint32_t sk[TILE][WORDS];
     __shared__ uint32_t sub[TILE];
     __shared__ int64_t row_b[TILE], row_e[TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * TILE;
+    const int64_t row0 = (block0 + (int64_t)blockIdx.x) * TILE;
     if (threadIdx.x < TILE) {
         const int64_t r = row0 + threadIdx.x;
         int64_t b = 0, e = 0;
@@ -549,7 +648,7 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         const int32_t* src = indices + row_b[row];
         const int len = (int)(row_e[row] - row_b[row]);   // a row has fewer than 2^31 columns
         uint32_t* dst = sk[row];
-        uint32_t in_h = 0;   // this lane's columns in H = those with the top hash bit set
+        uint32_t in_h = 0;   // this lane's columns in H1 (top hash bit set; low half) and in H2 (next bit; high half)
         for (int q = l8; q < len; q += 8 * PACK_LOADS) {
             int32_t col[PACK_LOADS];
 #pragma unroll
@@ -559,14 +658,14 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
                 if (col[t] >= 0) {   // column ids are non-negative
                     const uint32_t h = fold_hash((uint32_t)col[t], log2m);
                     atomicXor(&dst[h >> 5], 1u << (h & 31));
-                    in_h += h >> (log2m - 1);
+                    in_h += (h >> (log2m - 1)) + ((h << (18 - log2m)) & 0x10000u);
                 }
             }
         }
         if (in_h) atomicAdd(&sub[row], in_h);
     }
     __syncthreads();
-    uint32_t key = 0;
+    sortkey_t key = 0;
     if (threadIdx.x < TILE && row0 + threadIdx.x < n) {
         const int64_t r = row0 + threadIdx.x;
         uint32_t* out = sk_rows + (size_t)r * WORDS;
@@ -574,12 +673,11 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
         for (int g = 0; g < WORDS / 4; ++g)
             reinterpret_cast<uint4*>(out)[g] = make_uint4(sk[threadIdx.x][4 * g], sk[threadIdx.x][4 * g + 1],
                                                           sk[threadIdx.x][4 * g + 2], sk[threadIdx.x][4 * g + 3]);
-        key = sort_key(row_e[threadIdx.x] - row_b[threadIdx.x], sub[threadIdx.x]);
+        key = sort_key(row_e[threadIdx.x] - row_b[threadIdx.x], sub[threadIdx.x] & 0xffffu, sub[threadIdx.x] >> 16);
         keys[r] = key;
         vals[r] = (int32_t)r;
     }
-    key = __reduce_or_sync(0xffffffffu, key);
-    if (lane == 0 && key) atomicOr(or_key, key);
+    or_reduce_key(key, or_key);
 }
 
 // step 2 of 2 (after the sort): thread p of block `tile` fetches the staged sketch of the row at sorted position
@@ -1374,6 +1472,59 @@ __global__ void k_uf_merge_labels(int* __restrict__ parent, const int32_t* __res
     if (l != i) uf_unite(parent, i, l);
 }
 
+// ---- exchange steps of a multi-GPU pass (the collectives themselves are NCCL all-gathers issued by api.cu) ----
+// after the all-gather of the per-rank shares of the staged keys: row numbers and the OR word over ALL keys
+__global__ void __launch_bounds__(256) k_keys_finalize(const sortkey_t* __restrict__ keys, int64_t n, int32_t* __restrict__ vals,
+                                                       sortkey_t* __restrict__ or_key) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    sortkey_t k = 0;
+    if (i < n) {
+        k = keys[i];
+        vals[i] = (int32_t)i;
+    }
+    or_reduce_key(k, or_key);
+}
+
+// this rank's union-find as a compact list: one entry (row | root << 32) per row that is not its own root
+// (slot 0 of `mine` = the number of such rows; entries beyond `cap` are dropped and reported by the merge kernel)
+__global__ void __launch_bounds__(256) k_uf_compact(int* __restrict__ parent, int64_t n, unsigned long long* __restrict__ mine,
+                                                    unsigned long long cap) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int r = 0;
+    bool changed = false;
+    if (i < n) {
+        r = uf_find(parent, (int)i);
+        changed = r != (int)i;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, changed);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&mine[0], (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (changed) {
+            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) mine[1 + pos] = (unsigned long long)(uint32_t)i | ((unsigned long long)(uint32_t)r << 32);
+        }
+    }
+}
+
+// gathered[r] = the compact list of rank r ((cap + 1) words each): union(row, root) for every entry of every rank
+__global__ void __launch_bounds__(256) k_uf_merge_pairs(int* __restrict__ parent, const unsigned long long* __restrict__ gathered,
+                                                        int world, unsigned long long cap, unsigned int* __restrict__ fullest) {
+    const unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const int r = (int)(idx / cap);
+    if (r >= world) return;
+    const unsigned long long j = idx - (unsigned long long)r * cap;
+    const unsigned long long* lst = gathered + (size_t)r * (cap + 1);
+    const unsigned long long cnt = lst[0];
+    if (j == 0) atomicMax(fullest, (unsigned int)min(cnt, 0xffffffffull));
+    if (j < min(cnt, cap)) {
+        const unsigned long long e = lst[1 + j];
+        uf_unite(parent, (int)(uint32_t)e, (int)(uint32_t)(e >> 32));
+    }
+}
+
 // member lists (CSR): every member is united with the first member of its list
 __global__ void k_uf_lists(int* __restrict__ parent, const int64_t* __restrict__ list_indptr,
                            const int32_t* __restrict__ members, int64_t n_lists, int64_t n_members) {
@@ -1530,6 +1681,39 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                 const unsigned long long pos = pos0 + __popc(edge_mask & ((1u << lane) - 1u));
                 if (pos < edge_cap) edges[pos] = make_uint2((uint32_t)min(ra, rb), (uint32_t)max(ra, rb));
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Compact host form of the CSR ("CSR16", include/breakfast_b200.h): 32-bit row offsets, the low 16 bits of every column
+// and, per row, how many of its (ascending) columns are below 65536.  k_csr16_decode rebuilds the int64 / int32 CSR the
+// other kernels read: a warp per row, 128-bit stores where the row start allows.  HBM: reads 2 nnz + 6 N bytes, writes
+// 4 nnz + 8 N bytes (the host link carries half of what the plain form needs).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_csr16_decode(const uint32_t* __restrict__ indptr32, const uint16_t* __restrict__ split,
+                                                      const uint16_t* __restrict__ lo, int64_t n, int64_t* __restrict__ indptr,
+                                                      int32_t* __restrict__ indices) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp0 * 32; r0 <= n; r0 += n_warps * 32) {
+        // 32 rows per round: lane l fetches the extent of row r0 + l once, the warp then walks the rows
+        const int64_t r = r0 + lane;
+        uint32_t my_b = 0, my_e = 0, my_s = 0xffffffffu;
+        if (r <= n) {
+            my_b = __ldg(&indptr32[r]);
+            indptr[r] = (int64_t)my_b;
+            if (r < n) {
+                my_e = __ldg(&indptr32[r + 1]);
+                if (split) my_s = __ldg(&split[r]);
+            }
+        }
+        for (int l = 0; l < 32 && r0 + l < n; ++l) {
+            const uint32_t b = __shfl_sync(0xffffffffu, my_b, l), e = __shfl_sync(0xffffffffu, my_e, l);
+            const uint32_t sp = __shfl_sync(0xffffffffu, my_s, l);
+            for (uint32_t k = b + lane; k < e; k += 32)
+                indices[k] = (int32_t)((uint32_t)__ldg(&lo[k]) | (k - b >= sp ? 0x10000u : 0u));
         }
     }
 }

@@ -2,10 +2,13 @@
 
 The band tile pairs of the (upper-triangular) tile space are dealt cyclically to the ranks inside
 the pair kernel (work item w belongs to rank w % world, kernels.cuh k_pairs); every rank holds the
-whole packed matrix and runs a local union-find over the edges it found.  The only exchange step is
-the label merge: an all-gather of int32 labels[n_rows] per rank (NCCL over NVLink on GPUs) followed
-by a device-side re-union (k_uf_merge_labels).  torch is used for the collective and for device
-memory of the gathered buffer only.
+whole CSR and runs a local union-find over the edges it found.  Two exchange steps, both inside
+bf_run on the library's own NCCL communicator (include/breakfast_b200.h, "multi-GPU"): the shares of the
+sketch + sort-key pass are all-gathered (every rank streams 1/N of the rows), and after the verify
+step the ranks' union-finds are exchanged as compact (row, root) lists and re-united.  torch.distributed
+only carries the 128-byte communicator id (and the benchmark's barriers).  Without the library
+communicator (`lib_comm=False`, or a CPU process group in the tests) the older form remains: an
+all-gather of int32 labels[n_rows] per rank through torch.distributed + k_uf_merge_labels.
 """
 from __future__ import annotations
 
@@ -31,22 +34,40 @@ def gather_labels(local, group=None):
     return out
 
 
-class RankRunner:
-    """Drives one rank's context through run -> all-gather -> merge.  The context must have been
-    created on torch's current CUDA stream so that kernels and collectives are ordered."""
+def init_library_comm(ctx, rank: int, world: int, group=None) -> None:
+    """Give `ctx` the library's own NCCL communicator: rank 0 draws the id, torch.distributed broadcasts its 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    dev = torch.device("cuda", torch.cuda.current_device())
+    box = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        box.copy_(torch.frombuffer(bytearray(_native.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init_rank(bytes(box.cpu().numpy().tobytes()), rank, world)
 
-    def __init__(self, ctx, n_rows: int, rank: int, world: int, group=None):
+
+class RankRunner:
+    """Drives one rank's context through one pass per step.  With the library communicator (default on GPUs) a step is
+    just bf_run: the exchange steps happen inside it.  Otherwise run -> all-gather of the labels -> merge; the context
+    must then have been created on torch's current CUDA stream so that kernels and collectives are ordered."""
+
+    def __init__(self, ctx, n_rows: int, rank: int, world: int, group=None, lib_comm: bool = True):
         import torch
         self.ctx, self.n, self.rank, self.world, self.group = ctx, n_rows, rank, world, group
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.local = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
-        self.gathered = torch.empty((world, max(n_rows, 1)), dtype=torch.int32, device=dev) if world > 1 else None
+        self.local = self.gathered = None
+        if world > 1 and lib_comm and ctx.comm is None:
+            init_library_comm(ctx, rank, world, group)
+        if world > 1 and ctx.comm is None:
+            self.local = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+            self.gathered = torch.empty((world, max(n_rows, 1)), dtype=torch.int32, device=dev)
 
     def step(self, max_dist: int):
         """Enqueue one pass; returns nothing — call ctx.sync() for counters."""
         import torch.distributed as dist
         self.ctx.run(max_dist, self.rank, self.world)
-        if self.world > 1:
+        if self.world > 1 and getattr(self.ctx, "comm", None) is None:
             self.ctx.labels_to_device(self.local.data_ptr())
             if self.local.is_cuda:
                 dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
@@ -71,7 +92,8 @@ class RankRunner:
                     raise
                 over = 1
             if self.world > 1:
-                flag = torch.tensor([over], dtype=torch.int32, device=self.local.device)
+                dev = self.local.device if self.local is not None else torch.device("cuda", torch.cuda.current_device())
+                flag = torch.tensor([over], dtype=torch.int32, device=dev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
                 over = int(flag.item())
             if not over:

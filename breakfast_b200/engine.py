@@ -101,40 +101,73 @@ class ClusterResult:
 
 def _components_multi_device(indptr, indices, n_cols, max_dist, devices, want_edges, engine, query_rows=None,
                              lists=None) -> ClusterResult:
-    """Single-process multi-GPU: one host thread and one context per device, the band work items dealt
-    cyclically (rank r of len(devices)), labels merged on the first device (union(i, labels_r[i]))."""
+    """Single-process multi-GPU: one context and one host thread per device, the band work items dealt cyclically
+    (rank r of len(devices)).  On distinct devices the contexts share the library's NCCL communicator
+    (bf_comm_init_all): the sketch pass is sharded and the ranks' union-finds are merged over NVLink inside bf_run, so
+    every rank ends with the final labels and nothing but the first rank's labels crosses the host link.  Repeated
+    device ids (several ranks emulated on one GPU, tests) cannot form a communicator: their labels are merged through
+    the host (bf_merge_labels_host)."""
     import threading
     world = len(devices)
-    ctxs, stats, labels, edges, errors = [None] * world, [None] * world, [None] * world, [None] * world, []
-
-    def work(r):
-        try:
-            ctx = _native.Context(device=devices[r], engine=engine, want_edges=int(bool(want_edges)), **_context_options())
-            ctxs[r] = ctx
-            ctx.upload_csr(indptr, indices, n_cols, query_rows=query_rows)
-            stats[r] = ctx.run_sync(max_dist, rank=r, world=world)
-            labels[r] = ctx.download_labels()
-            if want_edges:
-                edges[r] = ctx.download_edges()
-        except BaseException as exc:  # re-raised in the caller's thread
-            errors.append(exc)
-
-    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    use_comm = len(set(devices)) == world
+    stats, labels, edges, errors = [None] * world, [None] * world, [None] * world, []
+    ctxs = []
     try:
+        for r in range(world):
+            ctxs.append(_native.Context(device=devices[r], engine=engine, want_edges=int(bool(want_edges)), **_context_options()))
+        if use_comm:
+            _native.comm_init_all(ctxs)
+        barrier = threading.Barrier(world)
+        overflowed = [False] * world
+
+        def work(r):
+            try:
+                ctx = ctxs[r]
+                ctx.upload_csr(indptr, indices, n_cols, query_rows=query_rows)
+                if not use_comm:
+                    stats[r] = ctx.run_sync(max_dist, rank=r, world=world)
+                    labels[r] = ctx.download_labels()
+                else:
+                    # a pass is collective: if any rank's bounded buffers overflowed (bf_sync raised them), all rerun
+                    for _ in range(6):
+                        ctx.run(max_dist, r, world)
+                        try:
+                            stats[r], overflowed[r] = ctx.sync(), False
+                        except _native.NativeError as exc:
+                            if exc.code != _native.BF_ERR_OVERFLOW:
+                                raise
+                            overflowed[r] = True
+                        barrier.wait()
+                        again = any(overflowed)
+                        barrier.wait()
+                        if not again:
+                            break
+                    else:
+                        raise _native.NativeError(_native.BF_ERR_OVERFLOW, "buffer overflow persisted on some device")
+                if want_edges:
+                    edges[r] = ctx.download_edges()
+            except BaseException as exc:  # re-raised in the caller's thread
+                errors.append(exc)
+                barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
         if errors:
-            raise errors[0]
+            real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+            raise (real or errors)[0]
         ctx0 = ctxs[0]
-        ctx0.merge_labels_host(np.stack(labels))
+        if not use_comm:
+            ctx0.merge_labels_host(np.stack(labels))
         if lists is not None and len(lists[0]) > 1:
             ctx0.union_lists(*lists)
         st = ctx0.sync().as_dict()
         st["n_edges"] = int(sum(s.n_edges for s in stats))
         st["n_candidates"] = int(sum(s.n_candidates for s in stats))
         st["n_gpus"] = world
+        st["label_merge"] = "nccl (in-library, over NVLink)" if use_comm else "host"
         out_labels = ctx0.download_labels()
         out_edges = None
         if want_edges:
@@ -145,8 +178,7 @@ def _components_multi_device(indptr, indices, n_cols, max_dist, devices, want_ed
         return ClusterResult(out_labels, st, out_edges)
     finally:
         for ctx in ctxs:
-            if ctx is not None:
-                ctx.close()
+            ctx.close()
 
 
 def components_full(indptr, indices, n_cols, max_dist, want_edges=False, device=None, engine=None) -> ClusterResult:

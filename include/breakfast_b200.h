@@ -106,7 +106,8 @@ void bf_ctx_destroy(bf_ctx* ctx);
  * single-chunk sketches; exact either way), "level1" (0 = level 1 on the integer
  * pipes, 1 = on the tensor cores: int8 mma.sync on +-1 expanded folds; 128/256-bit
  * sketches), "items_capacity" / "units_capacity" (entries of the expanded work list and
- * of the level-2 queue, 0 = automatic). */
+ * of the level-2 queue, 0 = automatic), "merge_capacity" (entries per rank of the compact label exchange of a
+ * multi-GPU pass, 0 = automatic). */
 int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
 
 /* ---- async, device-resident API (used by bench.py and the multi-rank host) */
@@ -122,6 +123,18 @@ int bf_upload_csr(bf_ctx* ctx, const int64_t* indptr, const int32_t* indices,
  * still running; the next bf_run waits for it and switches slots. */
 int bf_upload_csr_async(bf_ctx* ctx, const int64_t* indptr, const int32_t* indices,
                         int64_t n_rows, int32_t n_cols);
+/* Compact host form of a binary CSR ("CSR16"), half the bytes of the plain form on the host link: 32-bit row offsets
+ * `indptr32[n_rows + 1]`, the low 16 bits of every column `lo[nnz]` and, when n_cols > 65536, `split[n_rows]` = how many
+ * of a row's (ascending) columns are below 65536.  Representable when n_cols <= 131072, nnz < 2^32 and no row has more than
+ * 65535 columns - SARS-CoV-2 profiles (about 88 000 distinct mutations) are.  bf_csr16_encode fills caller-allocated
+ * arrays from the plain form (it validates the rows like bf_upload_csr; BF_ERR_INVALID when not representable);
+ * bf_upload_csr16_async is bf_upload_csr_async for this form: page-locked buffers, copy on the context's copy stream into
+ * the idle slot, decoded on the device (k_csr16_decode) behind the pass that is still running.  Same seam as
+ * bf_upload_csr: the scipy csr_matrix construction, breakfast.py:214. */
+int bf_csr16_encode(const int64_t* indptr, const int32_t* indices, int64_t n_rows, int32_t n_cols,
+                    uint32_t* indptr32_out, uint16_t* split_out /* may be NULL when n_cols <= 65536 */, uint16_t* lo_out);
+int bf_upload_csr16_async(bf_ctx* ctx, const uint32_t* indptr32, const uint16_t* split, const uint16_t* lo,
+                          int64_t n_rows, int32_t n_cols);
 /* Use a CSR that already lives in device memory owned by the caller (e.g. row shards that the ranks
  * uploaded in parallel and all-gathered over NVLink with torch.distributed).  Not copied; the caller
  * keeps it alive and orders its producers before bf_run on the context's stream. */
@@ -132,6 +145,25 @@ int bf_adopt_csr_device(bf_ctx* ctx, const void* indptr_device, const void* indi
  * kernel -> exact verify -> union-find -> labels (device).  Nothing is copied to
  * the host; call bf_sync to wait and read counters.  world >= 1, 0 <= rank < world. */
 int bf_run(bf_ctx* ctx, int32_t max_dist, int32_t rank, int32_t world);
+/* ---- multi-GPU: the library's own communicator (NCCL over NVLink / NVSwitch) ------------------------------------
+ * With a communicator, bf_run(ctx, d, rank, world) does the exchange steps of a multi-GPU pass itself, on the
+ * context's stream: (1) every rank streams only its share of the rows for the sketch + sort-key pass and the shares
+ * are all-gathered (24 bytes per row at 128 bits); (2) after verify + hook every rank publishes the rows of its
+ * union-find that are not their own root as (row, root) pairs, the lists are all-gathered and re-united, so that
+ * every rank ends with the same canonical labels.  Replaces the reference's single-process loop over cardinalities
+ * (breakfast.py:314-318) + networkx components (breakfast.py:325-326) for N GPUs; bf_labels_to_device /
+ * bf_merge_labels_* remain for callers that bring their own collective.  All ranks must call bf_run together.
+ * NCCL is bound at run time (dlopen of libnccl.so.2, or the path in BREAKFAST_B200_NCCL): BF_ERR_STATE if absent.
+ *   multi-process (one rank per process): rank 0 calls bf_comm_unique_id and hands the 128 bytes to the others by any
+ *     means, then every rank calls bf_ctx_comm_init_rank;
+ *   single process, one context per distinct device: bf_comm_init_all(ctxs, n) - rank i = ctxs[i]; the contexts are
+ *     then driven from one host thread each. */
+#define BF_COMM_ID_BYTES 128
+int bf_comm_unique_id(void* id_out /* BF_COMM_ID_BYTES */);
+int bf_ctx_comm_init_rank(bf_ctx* ctx, const void* id, int32_t rank, int32_t world);
+int bf_comm_init_all(bf_ctx** ctxs, int32_t n);
+int bf_ctx_comm_destroy(bf_ctx* ctx);
+
 /* D2D: copy this rank's labels (int32[n_rows], label = smallest row index of the
  * row's component as seen by this rank) into caller device memory, e.g. a torch
  * tensor that torch.distributed all-gathers over NCCL. */

@@ -174,16 +174,57 @@ def remap_cached_lists(cache, uniq):
     return kept, new_rows
 
 
+def lists_from_edges(n, rows, src, dst):
+    """neighbour lists (ascending, the row itself included - what the reference's radius query returns,
+    breakfast.py:226-228) of the rows `rows` (ascending) from an undirected edge list"""
+    rows = np.asarray(rows, dtype=np.int64)
+    a = np.concatenate([src, dst, rows]).astype(np.int64)
+    b = np.concatenate([dst, src, rows]).astype(np.int64)
+    wanted = np.zeros(n, dtype=bool)
+    wanted[rows] = True
+    keep = wanted[a]
+    a, b = a[keep], b[keep]
+    order = np.lexsort((b, a))
+    a, b = a[order], b[order]
+    bounds = np.searchsorted(a, np.concatenate([rows, [n]]))
+    return [b[bounds[i]:bounds[i + 1]] for i in range(len(rows))]
+
+
+def components_of_lists(n, lists):
+    """components(n, lists) without networkx (for 10^6 lists): every list chains its members (breakfast.py:103-113);
+    label = smallest row of the component; every row must occur in some list"""
+    import oracle
+    lengths = np.fromiter((len(l) for l in lists), dtype=np.int64, count=len(lists))
+    li = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
+    lm = np.concatenate([np.asarray(l, dtype=np.int32) for l in lists]) if len(lists) else np.zeros(0, np.int32)
+    seen = np.zeros(n, dtype=bool)
+    seen[lm] = True
+    assert seen.all(), "a row occurs in no neighbour list"
+    return oracle.components(n, None, None, li, lm).astype(np.int64)
+
+
 def cluster_table(ids, feats, sep2=" ", max_dist=1, min_cluster_size=2, cache=None, want_cache=False, core="sklearn"):
     """ids/filtered profile strings -> (text of clusters.tsv, cache dict or None).
     core="sklearn": the reference's own neighbour search (slow, hours beyond ~1e5 profiles);
     core="c": oracle.c brute force for the distance part (no cache support) — same results, pinned by
-    tests/test_oracle_golden.py::test_c_oracle_matches_ref_port and test_c_core_matches_goldens."""
+    tests/test_oracle_golden.py::test_c_oracle_matches_ref_port and test_c_core_matches_goldens;
+    core="hashjoin": oracle/hashjoin.py for the distance part (max_dist <= 2, 10^6 profiles in a minute), cache
+    supported: cached lists re-indexed as in cache.py:51-71, new rows queried against all rows (breakfast.py:294-304)."""
     uniq, codes, mult = dedup(feats)
     n = len(uniq)
     if max_dist == 0:
         labels = np.arange(n)
         lists = None
+    elif core == "hashjoin":
+        from oracle import hashjoin
+        indptr, indices, _ = binary_csr(uniq, sep2)
+        src, dst = hashjoin.edges(indptr, indices, max_dist)
+        if cache is not None and cache["max_dist"] == max_dist:
+            kept, new_rows = remap_cached_lists(cache, uniq)
+            lists = kept + lists_from_edges(n, sorted(new_rows), src, dst)
+        else:
+            lists = lists_from_edges(n, np.arange(n), src, dst)
+        labels = components_of_lists(n, lists)
     elif core == "c":
         import oracle
         assert cache is None and not want_cache

@@ -127,3 +127,74 @@ def scale_chain(recipe: dict) -> list:
     extra2["accession"] = ["new2_" + s for s in extra2["accession"]]
     df2 = pd.concat([extra2, df1[keep2]], ignore_index=True)
     return [d.to_csv(sep="\t", index=False) for d in (df0, df1, df2)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5 at their stated size (tests/golden/configs.json, made by tests/golden/make_config_golden.py)
+# ---------------------------------------------------------------------------------------------------------------
+CONFIG4_OPTS = dict(max_dist=1, sep2=",", id_col="seqName", clust_col="substitutions", var_type="nextclade_dna",
+                    skip_ins=True, skip_del=True, trim_start=3000, trim_end=3000)
+CONFIG5_OPTS = dict(max_dist=2, min_cluster_size=5)
+
+
+def config4_table(n=500_000) -> str:
+    """config 4: n unique nextclade_dna profiles with indels in the clustered column (several sequences per profile),
+    to be run with --skip-ins --skip-del and wide trims (profiles collapse)"""
+    from breakfast_b200 import synth
+    prof = synth.generate(n, seed=4, with_mult=True, unique_on_all_events=True)
+    return prof.table("nextclade_dna", ",", id_col="seqName", feature_col="substitutions").to_csv(sep="\t", index=False)
+
+
+def _new_substitution(rng, profile_tokens):
+    from breakfast_b200 import synth
+    while True:
+        pos = int(rng.integers(265, 29675))
+        ref = synth.ref_base(pos)
+        alt = "ACGT"[int(rng.integers(0, 4))]
+        tok = f"{ref}{pos}{alt}"
+        if alt != ref and tok not in profile_tokens:
+            return tok
+
+
+def config5_tables(n=1_000_000, n_delta=50_000, seed=5):
+    """config 5: (step 0 table, step 1 table).  Step 0 = n unique covsonar_dna profiles with multiplicities (config-3-like,
+    seed 5) plus a planted ghost triple.  Step 1 = step 0 with n_delta sequences touched: 60 % added (half of them new
+    unique profiles one or two substitutions away from an existing profile, half further sequences of existing
+    profiles), 20 % modified (their profile gains a substitution; a profile whose only sequence is modified vanishes), 20 %
+    deleted (most profiles have a single sequence, so whole profiles vanish and leave ghost lists), shuffled."""
+    from breakfast_b200 import synth
+    rng = np.random.default_rng(seed)
+    df0 = synth.generate(n, seed=seed, with_mult=True).table("covsonar_dna", " ")
+    a = "C1000T G2000A T3000C A4000G C5000T"
+    ghost = pd.DataFrame({"accession": ["ghostA1", "ghostA2", "ghostA3", "ghostA4", "ghostA5", "ghostX1",
+                                        "ghostB1", "ghostB2", "ghostB3", "ghostB4", "ghostB5"],
+                          "dna_profile": [a] * 5 + [a + " G6000A T7000C"] + [a + " G6000A T7000C A8000G C9000T"] * 5})
+    df0 = pd.concat([df0, ghost], ignore_index=True)
+    ids = df0["accession"].to_numpy(dtype=object)
+    feats = df0["dna_profile"].to_numpy(dtype=object)
+    m = len(df0)
+    n_add, n_mod, n_del = int(0.6 * n_delta), int(0.2 * n_delta), int(0.2 * n_delta)
+    touched = rng.choice(m - len(ghost), size=n_mod + n_del, replace=False)
+    mod_rows, del_rows = touched[:n_mod], touched[n_mod:]
+    feats1 = feats.copy()
+    for r in mod_rows:
+        toks = feats1[r].split(" ") if feats1[r] else []
+        feats1[r] = " ".join(toks + [_new_substitution(rng, set(toks))])
+    keep = np.ones(m, dtype=bool)
+    keep[del_rows] = False
+    keep[ids == "ghostX1"] = False                      # the bridge of the ghost triple disappears
+    src_rows = rng.choice(m - len(ghost), size=n_add, replace=False)
+    new_feats = []
+    for k, r in enumerate(src_rows):
+        if k % 2 == 0:                                  # a new profile at distance 1 or 2 of an existing one
+            toks = feats[r].split(" ") if feats[r] else []
+            extra = [_new_substitution(rng, set(toks))]
+            if k % 4 == 0:
+                extra.append(_new_substitution(rng, set(toks) | set(extra)))
+            new_feats.append(" ".join(toks + extra))
+        else:                                           # one more sequence of an existing profile
+            new_feats.append(feats[r])
+    added = pd.DataFrame({"accession": [f"add{k:06d}" for k in range(n_add)], "dna_profile": new_feats})
+    df1 = pd.concat([pd.DataFrame({"accession": ids[keep], "dna_profile": feats1[keep]}), added], ignore_index=True)
+    df1 = df1.iloc[rng.permutation(len(df1))].reset_index(drop=True)
+    return df0.to_csv(sep="\t", index=False), df1.to_csv(sep="\t", index=False)

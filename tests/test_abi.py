@@ -53,3 +53,32 @@ def test_no_device_means_error_not_fallback():
     assert e.value.code == _native.BF_ERR_NO_DEVICE
     g = C.c_double()
     assert lib.bf_measure_peak(0, b"popc32", C.byref(g)) == _native.BF_ERR_NO_DEVICE
+
+
+def test_csr16_encode_round_trip_and_limits():
+    """bf_csr16_encode (pure host code, no GPU needed): the compact form decodes back to the plain CSR; matrices that
+    do not fit it are refused"""
+    import numpy as np
+    import pytest
+    from breakfast_b200 import _native
+    rng = np.random.default_rng(5)
+    for n_cols in (300, 65536, 65537, 131072):
+        rows = [np.sort(rng.choice(n_cols, size=int(rng.integers(0, 120)), replace=False)) for _ in range(400)]
+        rows[7] = np.zeros(0, np.int64)
+        if n_cols > 65536:
+            rows[3] = np.unique(np.array([0, 65535, 65536, n_cols - 1]))
+        indptr = np.concatenate(([0], np.cumsum([len(r) for r in rows]))).astype(np.int64)
+        indices = np.concatenate(rows).astype(np.int32)
+        ip32, split, lo = _native.csr16_encode(indptr, indices, n_cols)
+        assert ip32.dtype == np.uint32 and lo.dtype == np.uint16 and np.array_equal(ip32, indptr)
+        assert (split is None) == (n_cols <= 65536)
+        pos = np.arange(indices.size) - np.repeat(indptr[:-1], np.diff(indptr))
+        hi = np.zeros(indices.size, np.int64) if split is None else (pos >= np.repeat(split.astype(np.int64), np.diff(indptr))) * 65536
+        assert np.array_equal(lo.astype(np.int64) + hi, indices)
+    indptr, indices = np.array([0, 2], np.int64), np.array([1, 200000], np.int32)
+    with pytest.raises(_native.NativeError):
+        _native.csr16_encode(indptr, indices, 200001)                       # too many columns
+    with pytest.raises(_native.NativeError):
+        _native.csr16_encode(np.array([0, 70000], np.int64), np.arange(70000, dtype=np.int32), 70000)   # row too long
+    with pytest.raises(_native.NativeError):
+        _native.csr16_encode(np.array([0, 2], np.int64), np.array([5, 5], np.int32), 10)                # not strictly ascending

@@ -169,3 +169,70 @@ def test_config5_incremental_1m_cached_plus_delta(million_mult):
     # ghost lists matter here: dropping them changes the partition
     assert not np.array_equal(oracle.components(n_cur, ws, wd), want) or list_members.size == 0
     assert res.stats["n_query"] == 6_000 and res.stats["pairs_total"] < 6_000 * n_cur
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# configs 4 and 5 at BASELINE's stated size, through the CLI; expected digests: tests/golden/configs.json
+# (tests/golden/make_config_golden.py: the reference's host steps restated + hash-join oracle, run on the CPU box)
+# ------------------------------------------------------------------------------------------------------------------
+import hashlib
+import json
+
+CONFIGS = json.loads((helpers.GOLDEN / "configs.json").read_text())
+
+
+def _sha(text):
+    return hashlib.sha256(text.encode()).hexdigest()
+
+
+def _cli(path, opts, outdir, cache_in=None, cache_out=None):
+    import click.testing
+    from breakfast_b200 import console
+    args = ["--input-file", str(path), "--outdir", str(outdir)] + helpers.cli_args(opts)
+    if cache_in:
+        args += ["--input-cache", str(cache_in)]
+    if cache_out:
+        args += ["--output-cache", str(cache_out)]
+    res = click.testing.CliRunner().invoke(console.main, args)
+    assert res.exit_code == 0, f"{res.output[-2000:]}\n{res.exception!r}"
+    return (outdir / "clusters.tsv").read_text()
+
+
+def test_config4_full_size_500k_nextclade_4_devices(tmp_path, monkeypatch):
+    """config 4 as BASELINE.json states it: 500 000 unique nextclade_dna profiles (833 990 sequences) with indels and
+    trimming, --skip-ins --skip-del, the pairwise work split over 4 ranks (four contexts on this GPU when the box has
+    fewer than four: BREAKFAST_B200_DEVICES=0,0,0,0), through console.main; clusters.tsv byte-identical to the CPU
+    oracle pipeline's (digest)."""
+    want = CONFIGS["config4"]
+    text = helpers.config4_table(want["n_profiles"])
+    assert _sha(text) == want["table_sha256"], "the generator drifted"
+    path = tmp_path / "c4.tsv"
+    path.write_text(text)
+    del text
+    n_dev = _native.device_count()
+    monkeypatch.setenv("BREAKFAST_B200_DEVICES", "0,1,2,3" if n_dev >= 4 else "0,0,0,0")
+    got = _cli(path, want["opts"], tmp_path / "out")
+    assert got.count("\n") == want["n_lines"]
+    assert _sha(got) == want["sha256"]
+
+
+def test_config5_full_size_1m_cache_plus_50k_delta_through_the_cli(tmp_path):
+    """config 5 as BASELINE.json states it: a first run over 1 000 000 unique profiles (1 667 179 sequences, --max-dist 2
+    --min-cluster-size 5) writes the reference-format cache; the second run gets a table with 50 000 sequences added,
+    modified or deleted (whole profiles vanish: ghost lists) and --input-cache, so only the new x all block is
+    evaluated.  Both outputs byte-identical to the CPU oracle pipeline's (digests); the cached answer differs from a
+    fresh run of the same table, as it does for the reference (ghost lists)."""
+    want = CONFIGS["config5"]
+    text0, text1 = helpers.config5_tables(want["n_profiles"], want["n_delta"])
+    assert [_sha(text0), _sha(text1)] == want["table_sha256"], "the generator drifted"
+    p0, p1 = tmp_path / "c5_0.tsv", tmp_path / "c5_1.tsv"
+    p0.write_text(text0)
+    p1.write_text(text1)
+    del text0, text1
+    cache = tmp_path / "cache" / "c5.cache"
+    got0 = _cli(p0, want["opts"], tmp_path / "o0", cache_out=cache)
+    assert got0.count("\n") == want["n_lines"][0] and _sha(got0) == want["sha256"][0]
+    del got0
+    got1 = _cli(p1, want["opts"], tmp_path / "o1", cache_in=cache)
+    assert got1.count("\n") == want["n_lines"][1] and _sha(got1) == want["sha256"][1]
+    assert want["fresh_step1_sha256"] != want["sha256"][1]

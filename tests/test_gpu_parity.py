@@ -190,8 +190,8 @@ def test_schedule_counter_matches_the_cpu_mirror(max_dist):
     with _native.Context(sketch_bits=128) as ctx:
         ctx.upload_csr(indptr, indices, n_cols)
         st = ctx.run_sync(max_dist)
-    assert st.tiles_band == schedule_sim.tile_pairs(indptr, indices, max_dist, 2)
-    assert st.tiles_band < schedule_sim.tile_pairs(indptr, indices, max_dist, 1)
+    assert st.tiles_band == schedule_sim.tile_pairs(indptr, indices, max_dist, 3)
+    assert st.tiles_band < schedule_sim.tile_pairs(indptr, indices, max_dist, 2) < schedule_sim.tile_pairs(indptr, indices, max_dist, 1)
 
 
 def _near_duplicate_rows(n, card, n_cols, seed, spread):
@@ -455,6 +455,56 @@ def test_async_double_buffered_upload_and_adopted_device_csr():
             ctx.adopt_csr_device(d_ip.data_ptr(), d_ix.data_ptr(), len(ip) - 1, nc, ix.size)
             ctx.run_sync(1)
             assert np.array_equal(ctx.download_labels(), wants[1])
+
+
+def _pinned_copy(lib, arr):
+    q = C.c_void_p()
+    assert lib.bf_pinned_alloc(max(arr.nbytes, 1), C.byref(q)) == 0
+    C.memmove(q, arr.ctypes.data, arr.nbytes)
+    return q
+
+
+@pytest.mark.parametrize("wide", [False, True], ids=["cols<=65536", "cols>65536"])
+def test_compact_csr16_upload_gives_the_plain_answer(wide):
+    """bf_csr16_encode + bf_upload_csr16_async (16-bit columns + per-row split, decoded on the device) alternating with
+    the plain async upload on the two slots: every batch gets the oracle's labels and edges"""
+    lib = _native.load()
+    batches = []
+    for n, seed in ((9000, 21), (12000, 22)):
+        ip, ix, nc = synth.generate(n, seed=seed).csr()
+        if wide:   # spread the columns over 0 .. 131071 (order kept), so that most rows straddle the 65536 boundary
+            nc2 = 131072
+            ix = (ix.astype(np.int64) * (nc2 - 1) // max(nc - 1, 1)).astype(np.int32)
+            nc = nc2
+        batches.append((ip, ix, nc))
+    if wide:
+        assert any((batches[0][1] < 65536).any() and (batches[0][1] >= 65536).any() for _ in [0])
+    wants = [oracle.cluster(ip, ix, 1)[0] for ip, ix, _ in batches]
+    pinned = []
+    for ip, ix, nc in batches:
+        ip32, split, lo = _native.csr16_encode(ip, ix, nc)
+        assert (split is not None) == wide
+        pinned.append((_pinned_copy(lib, ip32), _pinned_copy(lib, split) if split is not None else None, _pinned_copy(lib, lo),
+                       _pinned_copy(lib, ip), _pinned_copy(lib, ix)))
+    with _native.Context(want_edges=1) as ctx:
+        for k in range(5):
+            cur = k % 2
+            ip, ix, nc = batches[cur]
+            q = pinned[cur]
+            if k == 3:     # plain form in between: the slots alternate whatever the form
+                ctx.upload_csr_async_ptr(q[3].value, q[4].value, len(ip) - 1, nc)
+            else:
+                ctx.upload_csr16_async_ptr(q[0].value, q[1].value if q[1] is not None else None, q[2].value, len(ip) - 1, nc)
+            ctx.run(1)
+            ctx.sync()
+            assert np.array_equal(ctx.download_labels(), wants[cur]), k
+        src, dst = ctx.download_edges()
+        ws, wd = oracle.edges(batches[0][0], batches[0][1], 1)
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+    for q in pinned:
+        for x in q:
+            if x is not None:
+                lib.bf_pinned_free(x)
 
 
 def test_measured_pipe_peaks_are_plausible():
