@@ -158,6 +158,98 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# extra measurements of the N = 1 line: other configs, CLI wall-clock, FULL-engine POPC roofline
+# ------------------------------------------------------------------------------------------------
+def time_device_steps(_native, stream, csr, max_dist, query_rows=None, steps=5, warmup=3, **opts):
+    """ms per device-resident pass (CUDA events inside the library, summed over `steps` passes) + counters"""
+    indptr, indices, n_cols = csr
+    with _native.Context(device=0, stream=stream, **opts) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols, query_rows=query_rows)
+        for _ in range(warmup):
+            ctx.run_sync(max_dist)
+        for _ in range(steps):
+            ctx.run(max_dist)
+        st = ctx.sync()
+    return st.ms_total_sum / max(1, min(st.runs_since_sync, 128)), st
+
+
+def measure_configs(_native, stream, np):
+    """device step of BASELINE configs 2-5 at their stated shapes (parity of each: tests/test_gpu_configs.py)"""
+    from breakfast_b200 import synth
+    out = {}
+    ms, st = time_device_steps(_native, stream, synth.generate(100_000, seed=2).csr(), 1)
+    out["config2_100k_d1"] = {"ms_per_step": ms, "candidate_pairs": st.pairs_band, "edges": st.n_edges}
+    c3 = synth.generate(1_000_000, seed=3, with_mult=True).csr()
+    ms, st = time_device_steps(_native, stream, c3, 2)
+    out["config3_1m_d2"] = {"ms_per_step": ms, "candidate_pairs": st.pairs_band, "edges": st.n_edges, "tiles_band": st.tiles_band}
+    ms, st = time_device_steps(_native, stream, synth.generate(500_000, seed=4, with_mult=True, unique_on_all_events=True).csr(), 1)
+    out["config4_500k_nextclade_shape_d1"] = {"ms_per_step": ms, "candidate_pairs": st.pairs_band, "edges": st.n_edges}
+    q = np.sort(np.random.default_rng(5).choice(1_000_000, size=50_000, replace=False)).astype(np.int32)
+    ms, st = time_device_steps(_native, stream, c3, 2, query_rows=q)
+    out["config5_rectangle_50k_x_1m_d2"] = {"ms_per_step": ms, "candidate_pairs": st.pairs_band, "edges": st.n_edges}
+    return out
+
+
+def measure_full_engine_roofline(_native, stream, peaks):
+    """the literal north-star kernel (FULL engine: every column as a bit, tiled XOR/POPC, executed == algorithmic work)
+    against the POPC pipe peak measured in this process, at a size that fits the time budget"""
+    from breakfast_b200 import synth
+    csr = synth.generate(100_000, seed=1).csr()
+    ms, st = time_device_steps(_native, stream, csr, 1, steps=3, warmup=2, engine="full")
+    ms_pairs = st.ms_pairs_sum / max(1, min(st.runs_since_sync, 128))
+    gpopc = st.popc32_executed / (ms_pairs * 1e-3) / 1e9
+    return {"kernel": f"k_pairs<4> (FULL engine, {st.bits_per_row} bits/row, 100 000 profiles)", "bound": "int_pipe_popc",
+            "achieved": gpopc, "peak": peaks["popc32"], "unit": "GPOPC32/s", "frac": gpopc / peaks["popc32"], "ms_per_launch": ms_pairs,
+            "popc32_per_launch": st.popc32_executed, "pairs_evaluated": st.pairs_evaluated}
+
+
+def measure_cli_wall(n_profiles):
+    """wall-clock of the product CLI (console.main) on the headline table: n unique profiles, one sequence each"""
+    import tempfile
+    import click.testing
+    from breakfast_b200 import console, synth
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        t0 = time.perf_counter()
+        table = synth.generate(n_profiles, seed=SEED).table("covsonar_dna", " ")
+        path = tmp / "table.tsv"
+        table.to_csv(path, sep="\t", index=False)
+        t_make = time.perf_counter() - t0
+        size = path.stat().st_size
+        del table
+        res = click.testing.CliRunner().invoke(console.main, ["--input-file", str(path), "--outdir", str(tmp / "out"), "--max-dist", str(MAX_DIST)])
+        if res.exit_code != 0:
+            return {"error": f"CLI failed: {res.exception!r}"}
+        t = dict(console.LAST_TIMINGS)
+        clustered = sum(1 for line in open(tmp / "out" / "clusters.tsv") if not line.rstrip("\n").endswith("\t")) - 1
+    host = t["total"] - t.get("engine", 0.0)
+    return {"cli_wall_s": t["total"], "host_s": host, "stages_s": {k: t[k] for k in ("read", "prepare", "cluster", "write")},
+            "engine_s": t.get("engine"), "host_path": t.get("host_path"), "sequences": n_profiles, "table_bytes": size,
+            "clustered_sequences": clustered, "table_generation_s": t_make,
+            "note": "read = pandas read_table; prepare = filter + dedup + CSR (native host pass); cluster = engine (H2D, kernels, "
+                    "D2H; engine_s) + labelling; write = clusters.tsv"}
+
+
+def measure_port_stages(n_sequences=30_000):
+    """per-stage host times of the oracle port (the reference's host steps restated) on a bounded sample, for the split
+    next to cli_wall_s (BASELINE.md section 3 iii)"""
+    import tempfile
+    from breakfast_b200 import synth
+    from oracle import ref_port
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "t.tsv"
+        synth.generate(n_sequences, seed=SEED).table("covsonar_dna", " ").to_csv(path, sep="\t", index=False)
+        t = {}
+        t0 = time.perf_counter(); ids, feats = ref_port.read(path); t["read"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); feats = ref_port.filter_profiles(feats, " ", "covsonar_dna", True, True, 264, 228, 29903); t["filter"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); uniq, codes, mult = ref_port.dedup(feats); t["dedup"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); ref_port.count_matrix(uniq, " "); t["vectorise"] = time.perf_counter() - t0
+    return {"sequences": n_sequences, "stages_s": t, "us_per_sequence": {k: 1e6 * v / n_sequences for k, v in t.items()},
+            "kind": "port", "note": "single-threaded Python, as in the reference; the neighbour search is the cpu_baseline"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -171,6 +263,7 @@ def main():
     ap.add_argument("--level1", type=int, default=1, choices=[0, 1], help="1 = int8 mma.sync level 1 (default), 0 = integer pipes")
     ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs_ms / cli_wall_s / full-engine roofline (N = 1 extras)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -233,7 +326,7 @@ def main():
     p_labels = C.c_void_p()
     assert lib.bf_pinned_alloc(labels_host.nbytes, C.byref(p_labels)) == 0
 
-    peaks = {name: _native.measure_peak(name, local_rank) for name in ("popc32", "lop3", "imma_s8")}  # also warms the clocks
+    peaks = {name: _native.measure_peak(name, local_rank) for name in ("popc32", "lop3", "imma_s8", "umma_i8")}  # also warms the clocks
 
     # a real (non-default) torch stream: the library enqueues on it, torch events and NCCL order against it
     tstream = torch.cuda.Stream()
@@ -283,8 +376,13 @@ def main():
         ops_per_launch = int(st.pairs_evaluated * 32)
         achieved = ops_per_launch / (ms_kernel * 1e-3) / 1e9
         extra = {"macs_per_pair": 32, "level2_units": st.l2_warp_items, "ms_level2": (st.ms_pairs_sum - st.ms_l1_sum) / runs,
-                 "note": "tcgen05 peak is 4x the mma.sync rate, but with K = 32 its TMEM accumulator round trip is exposed "
-                         "(tools/experiments/l1_tcgen05_kernel.cuh.txt); the register-accumulator path is the faster one here"}
+                 "tcgen05_int8_peak": peaks["umma_i8"], "frac_of_tcgen05_int8_peak": achieved / peaks["umma_i8"],
+                 "note": "side by side: frac = of the int8 rate reachable with register accumulators (mma.sync), "
+                         "frac_of_tcgen05_int8_peak = of the tcgen05.mma kind::i8 rate measured in this process (UTCIMMA, TMEM "
+                         "accumulators).  The tcgen05 form of this kernel was built and instrumented twice (profiles/r02_tcgen05_*.log): "
+                         "every pair costs one TMEM -> register read, TMEM holds 65 536 accumulators and one accumulator round trip "
+                         "(issue -> MMA -> commit -> wake -> tcgen05.ld -> release -> wake) takes >= 1000 cycles at K <= 128, so it peaks "
+                         "at 12-18 pairs/clk/SM against 35 for this kernel"}
     elif two_kernel:
         # dominant kernel = k_pairs_l1<T>.  Per evaluated pair it executes:
         #   T = max_dist in {1,2}: 1 XOR + T/2 AND + 1/2 min on the ALU pipe, 1/2 POPC on the XU pipe, T/2 IMAD (FMA)
@@ -392,10 +490,20 @@ def main():
             ix = indices[: ip[-1]]
             X = csr_matrix((_np.ones(ix.size, dtype=_np.int64), ix.astype(_np.int64), ip), shape=(ns, n_cols))
             band = pairs_band_of(_np.diff(ip), MAX_DIST)
-            sec, evals, _ = cpu_step(X)
-            cpu = {"value": band / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            cold, _, _ = cpu_step(X)            # first call: imports scikit-learn, spins up its thread pool
+            sec, evals, _ = cpu_step(X)         # warm: what the reference arm (--impl reference) also reports
+            cpu = {"value": band / sec, "unit": UNIT, "cores": cores, "kind": "port", "cold_first_call_s": cold,
                    "sample": f"first {ns} profiles of the workload: {band} candidate pairs, {evals} ordered distance "
-                             f"evaluations (reference batches through scikit-learn), {sec:.1f} s"}
+                             f"evaluations (reference batches through scikit-learn), {sec:.1f} s warm ({cold:.1f} s for the cold first call)"}
+        extras = {}
+        if world == 1 and not args.no_extras and n == N_PROFILES:
+            try:
+                extras["configs_ms"] = measure_configs(_native, stream, np)
+                extras["full_engine_roofline"] = measure_full_engine_roofline(_native, stream, peaks)
+                extras["cli"] = measure_cli_wall(n)
+                extras["cli"]["port_stages"] = measure_port_stages()
+            except Exception as exc:   # the headline numbers above are already taken; say what went wrong
+                extras["extras_error"] = repr(exc)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -404,7 +512,7 @@ def main():
                        "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level), "level1": "imma" if args.level1 == 1 else "int_pipes",
                        "l2_warp_items": st.l2_warp_items, "pairs_evaluated": st.pairs_evaluated, "n_cols": n_cols, "nnz": int(indices.size),
                        "candidate_pairs": st.pairs_band, "pairs_total": st.pairs_total, "tiles_band": st.tiles_band,
-                       "edges": None if world > 1 else st.n_edges, "components": st.n_components,
+                       "edges": None if world > 1 else st.n_edges, "components": st.n_components, "sketch_survivors_rank0": st.n_candidates,
                        "l2_policy": "inputs larger than L2 (CSR 360 MB + per-step rebuilt bitsets); no explicit flush",
                        "parallelism": f"tile-partition x{world}" if world > 1 else "single GPU"},
             "clocks": clock_info,
@@ -425,6 +533,7 @@ def main():
             "cpu_baseline": cpu,
             "phases_ms": {k: getattr(st, k) for k in ("ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge")},
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     ctx.close()
     for p in (p_indptr, p_indices, p_labels) + (tuple(csr16[0]) if csr16 else ()):

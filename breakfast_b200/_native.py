@@ -14,7 +14,8 @@ from . import build as _build
 
 ENGINE_SKETCH = 0
 ENGINE_FULL = 1
-_ENGINES = {"sketch": ENGINE_SKETCH, "full": ENGINE_FULL, 0: 0, 1: 1}
+ENGINE_HASHJOIN = 2
+_ENGINES = {"sketch": ENGINE_SKETCH, "full": ENGINE_FULL, "hashjoin": ENGINE_HASHJOIN, 0: 0, 1: 1, 2: 2}
 
 BF_OK = 0
 BF_ERR_INVALID = -1

@@ -26,6 +26,11 @@ from scipy.sparse import csr_matrix
 from . import cache as ca
 from . import engine
 
+import time
+
+# seconds the last cluster_features call spent inside the engine (H2D, kernels, D2H) - the rest of its time is host work
+LAST_ENGINE_TIMINGS: dict = {}
+
 
 # --------------------------------------------------------------------------------------------
 # I/O
@@ -270,6 +275,7 @@ def cluster_features(meta, feature_sep, max_dist, min_cluster_size, input_cache,
         )
 
     want_edges = bool(output_cache)
+    t_engine = time.perf_counter()
     if cached is None:
         result = engine.components_full(indptr, indices, n_cols, max_dist, want_edges=want_edges)
         list_rows = np.arange(n)
@@ -282,6 +288,8 @@ def cluster_features(meta, feature_sep, max_dist, min_cluster_size, input_cache,
         list_rows = new_rows
         kept_lists = [list_members[list_indptr[i]:list_indptr[i + 1]].astype(np.int64)
                       for i in range(len(list_indptr) - 1)] if want_edges else []
+    LAST_ENGINE_TIMINGS.clear()
+    LAST_ENGINE_TIMINGS.update(engine=time.perf_counter() - t_engine)
 
     if output_cache:
         src, dst = result.edges

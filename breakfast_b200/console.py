@@ -13,7 +13,12 @@ from click.core import ParameterSource
 
 from . import __version__, breakfast
 
+import time
+
 VAR_TYPES = ("covsonar_dna", "covsonar_aa", "nextclade_dna", "nextclade_aa", "raw")
+# wall-clock of the five pipeline steps of the last run (seconds), for benchmarks: read, prepare (filter + dedup
+# [+ CSR on the native host path]), cluster (CSR if not done yet, engine, cache, labels), write
+LAST_TIMINGS: dict = {}
 DNA_TYPES = ("covsonar_dna", "nextclade_dna")
 
 
@@ -94,7 +99,10 @@ def run(input_file, outdir, input_cache, output_cache, id_col, clust_col, var_ty
 
     os.environ["OMP_NUM_THREADS"] = str(jobs)
 
+    LAST_TIMINGS.clear()
+    t0 = time.perf_counter()
     meta = breakfast.read_input(input_file, sep, id_col, clust_col)
+    t1 = time.perf_counter()
     meta_nodups, pre = None, None
     if os.environ.get("BREAKFAST_B200_HOST", "native") == "native" and var_type in VAR_TYPES:
         # one native pass (csrc/host_parse.cpp) instead of three Python loops over every token; same result
@@ -108,8 +116,13 @@ def run(input_file, outdir, input_cache, output_cache, id_col, clust_col, var_ty
             meta["feature"], sep2, var_type, skip_ins, skip_del, trim_start, trim_end, reference_length
         )
         meta_nodups = breakfast.collapse_duplicates(meta)
+    t2 = time.perf_counter()
     meta_clustered = breakfast.cluster(meta_nodups, sep2, max_dist, min_cluster_size, input_cache, output_cache, pre=pre)
+    t3 = time.perf_counter()
     breakfast.write_output(meta_clustered, meta, outdir)
+    t4 = time.perf_counter()
+    LAST_TIMINGS.update(read=t1 - t0, prepare=t2 - t1, cluster=t3 - t2, write=t4 - t3, total=t4 - t0,
+                        host_path="native" if pre is not None else "python", **breakfast.LAST_ENGINE_TIMINGS)
 
 
 main = click.version_option(version=__version__)(

@@ -186,6 +186,7 @@ struct bf_ctx {
     // other) or caller-owned memory (bf_adopt_csr_device); d_indptr/d_indices is what kernels read
     DevBuf indptr[2], indices[2], query_rows, is_query;
     DevBuf c16_indptr[2], c16_split[2], c16_lo[2];   // staging of the compact host form, one set per slot
+    DevBuf hj_hash, hj_t1, hj_t2, hj_t2_rows;        // hash-join engine: row hashes, row table, one-deletion table
     const int64_t* d_indptr = nullptr;
     const int32_t* d_indices = nullptr;
     int cur = 0, pending = -1;
@@ -493,6 +494,50 @@ int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int
     return BF_OK;
 }
 
+inline unsigned long long hj_capacity(int64_t want) {
+    unsigned long long cap = 1024;
+    while ((int64_t)cap < want) cap <<= 1;
+    return cap;
+}
+
+// K7: the joins of the hash-join engine -> candidates (row numbers) for k_verify_unite.  This rank probes the rows
+// r = rank (mod world); the tables hold all rows.
+int run_hashjoin_probes(bf_ctx* c) {
+    const int64_t n = c->n_rows;
+    const int d = c->max_dist;
+    const unsigned long long cap1 = hj_capacity(2 * n);
+    const unsigned long long* H = c->hj_hash.as<unsigned long long>();
+    const unsigned long long* t1 = c->hj_t1.as<unsigned long long>();
+    const unsigned char* isq = c->has_query ? c->is_query.as<unsigned char>() : nullptr;
+    uint2* cand = c->cand.as<uint2>();
+    DevCounters* dc = c->counters.as<DevCounters>();
+    const int64_t my_rows = ceil_div(n, c->world);
+    k_hj_probe_equal<<<grid_for(my_rows, 256), 256, 0, c->stream>>>(c->d_indptr, n, H, t1, cap1 - 1, c->rank, c->world, isq, cand, c->cand_cap_used, dc);
+    CKLC(c);
+    if (d >= 1) {
+        k_hj_probe_deletions<1><<<grid_for(my_rows * 8, 256), 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, H, t1, nullptr, cap1 - 1, c->rank,
+                                                                                   c->world, isq, cand, c->cand_cap_used, dc);
+        CKLC(c);
+    }
+    if (d >= 2) {
+        k_hj_probe_pairs<<<grid_for(my_rows * 32, 256), 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, H, t1, cap1 - 1, c->rank, c->world, isq, cand,
+                                                                             c->cand_cap_used, dc);
+        CKLC(c);
+        const unsigned long long cap2 = hj_capacity(2 * std::max<int64_t>(c->nnz, 1));
+        TRY(c->hj_t2.ensure((size_t)cap2 * sizeof(unsigned long long)));
+        TRY(c->hj_t2_rows.ensure((size_t)cap2 * sizeof(int32_t)));
+        CK(cudaMemsetAsync(c->hj_t2.p, 0xff, (size_t)cap2 * sizeof(unsigned long long), c->stream));
+        k_hj_build_deletions<<<grid_for(n * 8, 256), 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, H, c->hj_t2.as<unsigned long long>(),
+                                                                          c->hj_t2_rows.as<int32_t>(), cap2 - 1);
+        CKLC(c);
+        k_hj_probe_deletions<2><<<grid_for(my_rows * 8, 256), 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, H, c->hj_t2.as<unsigned long long>(),
+                                                                                   c->hj_t2_rows.as<int32_t>(), cap2 - 1, c->rank, c->world, isq, cand,
+                                                                                   c->cand_cap_used, dc);
+        CKLC(c);
+    }
+    return BF_OK;
+}
+
 int finish_labels(bf_ctx* c) {
     const int64_t n = c->n_rows;
     if (n == 0) return BF_OK;
@@ -584,7 +629,7 @@ void bf_ctx_destroy(bf_ctx* c) {
         c->comm = nullptr;
     }
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query,
-                      &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->keysB[0], &c->keysB[1], &c->keysB[2],
+                      &c->hj_hash, &c->hj_t1, &c->hj_t2, &c->hj_t2_rows, &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->keysB[0], &c->keysB[1], &c->keysB[2],
                       &c->valsB[0], &c->valsB[1], &c->valsB[2], &c->keysA[0], &c->keysA[1], &c->keysA[2], &c->valsA[0], &c->valsA[1], &c->valsA[2], &c->sched_table,
                       &c->sort_counts, &c->sort_max, &c->sk_rows, &c->xchg, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
@@ -605,7 +650,8 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     if (!c || !key) return fail(BF_ERR_INVALID, "null argument");
     std::string k(key);
     if (k == "engine") {
-        if (value != BF_ENGINE_SKETCH && value != BF_ENGINE_FULL) return fail(BF_ERR_INVALID, "engine must be 0 (sketch) or 1 (full)");
+        if (value != BF_ENGINE_SKETCH && value != BF_ENGINE_FULL && value != BF_ENGINE_HASHJOIN)
+            return fail(BF_ERR_INVALID, "engine must be 0 (sketch), 1 (full) or 2 (hash join)");
         c->engine = (int)value;
     } else if (k == "sketch_bits") {
         if (value < 128 || value > 2048 || (value & (value - 1))) return fail(BF_ERR_INVALID, "sketch_bits must be a power of two in [128, 2048]");
@@ -830,6 +876,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     if (c->comm && world > 1 && (rank != c->comm_rank || world != c->comm_world))
         return fail(BF_ERR_INVALID, "rank/world differ from the communicator of this context");
     if (c->comm && world > 1 && !bfnccl::api().ok) return fail(BF_ERR_STATE, bfnccl::api().error);
+    if (c->engine == BF_ENGINE_HASHJOIN && max_dist > 2) return fail(BF_ERR_INVALID, "the hash-join engine covers max_dist 0, 1 and 2");
     TRY(set_device(c));
     if (c->pending >= 0) {
         // the CSR of this pass was uploaded asynchronously into the idle slot: order after the copy
@@ -851,7 +898,12 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     c->ms_merge = 0;
     const int64_t nB = c->n_rows, nA = c->n_query;
 
-    if (c->engine == BF_ENGINE_SKETCH) {
+    const bool hashjoin = c->engine == BF_ENGINE_HASHJOIN;
+    if (hashjoin) {
+        c->K4 = 1;
+        c->n_chunks = 1;
+        c->bits_per_row = 64;   // the additive row hash
+    } else if (c->engine == BF_ENGINE_SKETCH) {
         const int words = c->sketch_bits / 32;
         c->K4 = std::min(4, words / 4);
         c->n_chunks = words / (4 * c->K4);
@@ -886,7 +938,17 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         TRY(ensure_sort_buffers(c, std::max(nB, staged_pack(c) ? staged_rows(c) : nB), c->keysB, c->valsB));
         if (c->has_query) TRY(ensure_sort_buffers(c, nA, c->keysA, c->valsA));
         const bool staged = staged_pack(c);
-        if (staged) {
+        if (hashjoin) {   // rows are only sorted by cardinality here, for the candidate-pair statistic of the metric
+            TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0, false));
+            if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1, false));
+            DevCounters* dc = c->counters.as<DevCounters>();
+            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, &dc->band_ab);
+            CKLC(c);
+            if (c->has_query) {
+                k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, keysA[0].as<sortkey_t>(), nA, max_dist, &dc->band_aa);
+                CKLC(c);
+            }
+        } else if (staged) {
             TRY(pack_stage_all_rows(c));
             if (c->has_query) {   // before the sort of the B side reuses keysB[0]
                 k_gather_keys<<<grid_for(nA, 256), 256, 0, c->stream>>>(c->keysB[0].as<sortkey_t>(), c->query_rows.as<int32_t>(), nA,
@@ -895,17 +957,36 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
                 CKLC(c);
             }
         }
-        TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0, staged));
-        if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1, staged));
+        if (!hashjoin) {
+            TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0, staged));
+            if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1, staged));
+        }
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
-    if (active) {
+    if (active && hashjoin) {
+        // ---- K7: row hashes + the row table
+        const unsigned long long cap1 = hj_capacity(2 * nB);
+        TRY(c->hj_hash.ensure((size_t)nB * sizeof(unsigned long long)));
+        TRY(c->hj_t1.ensure((size_t)cap1 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->hj_t1.p, 0xff, (size_t)cap1 * sizeof(unsigned long long), c->stream));
+        k_hj_hash_rows<<<grid_for(nB * 8, 256), 256, 0, c->stream>>>(c->d_indptr, c->d_indices, nB, c->hj_hash.as<unsigned long long>(),
+                                                                     c->hj_t1.as<unsigned long long>(), cap1 - 1);
+        CKLC(c);
+    }
+    if (active && !hashjoin) {
         // ---- K1: bit-pack
         TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB, c->fold8B));
         if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA, c->fold8A));
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
-    if (active) {
+    if (active && hashjoin) {
+        unsigned long long cap = c->cand_capacity > 0 ? (unsigned long long)c->cand_capacity
+                                                      : (unsigned long long)std::max<int64_t>((int64_t)1 << 22, 8 * nB);
+        TRY(c->cand.ensure((size_t)cap * sizeof(uint2)));
+        c->cand_cap_used = cap;
+        if (c->want_edges) TRY(c->edges.ensure((size_t)cap * sizeof(uint2)));
+    }
+    if (active && !hashjoin) {
         // ---- K2b: schedule
         // three sort keys where the sketch pass produced them and the (D, Ds) table stays small, else the plain band
         const int n_keys = staged_pack(c) ? (max_dist <= kThreeKeyMaxDist ? 3 : 2) : 1;
@@ -969,7 +1050,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     }
     CK(cudaEventRecord(c->ev[3], c->stream));
     CK(cudaEventRecord(ring[1], c->stream));
-    if (active) {
+    if (active && hashjoin) TRY(run_hashjoin_probes(c));
+    if (active && !hashjoin) {
         // ---- K3: pairs
         const uint4* A = (c->has_query ? c->bitsA : c->bitsB).as<uint4>();
         const uint4* B = c->bitsB.as<uint4>();
@@ -992,9 +1074,9 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         int vbps = 0;   // grid-stride kernel: launch exactly the blocks that are resident at once
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, verify, 256, 0));
         verify<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
-            c->cand.as<uint2>(), c->cand_cap_used, valsA[0].as<int32_t>(), c->valsB[0].as<int32_t>(),
+            c->cand.as<uint2>(), c->cand_cap_used, hashjoin ? nullptr : valsA[0].as<int32_t>(), hashjoin ? nullptr : c->valsB[0].as<int32_t>(),
             c->d_indptr, c->d_indices, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
-            c->has_query ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
+            (c->has_query && !hashjoin) ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
             c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
         CKLC(c);
     }

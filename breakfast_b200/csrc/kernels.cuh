@@ -1570,8 +1570,8 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
         bool keep = false;
         if ((unsigned long long)lane < batch && c < n) {
             const uint2 pr = cand[c];
-            ra = permA[pr.x];
-            rb = permB[pr.y];
+            ra = permA ? permA[pr.x] : (int)pr.x;   // the hash-join engine emits row numbers, the tile engines sorted positions
+            rb = permB ? permB[pr.y] : (int)pr.y;
             keep = true;
             if (is_query) keep = (ra != rb) && !(is_query[rb] && ra > rb);
         }
@@ -1716,6 +1716,227 @@ __global__ void __launch_bounds__(256) k_csr16_decode(const uint32_t* __restrict
                 indices[k] = (int32_t)((uint32_t)__ldg(&lo[k]) | (k - b >= sp ? 0x10000u : 0u));
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: hash-join engine (max_dist <= 2) - exact candidate generation in O(nnz * m^(d-1)) probes instead of tile pairs.
+// Two different rows A, B (ascending unique columns) are at distance
+//     1  iff  one is the other minus one column,
+//     2  iff  one is the other minus two columns ("superset"), or |A| = |B| and A minus some x equals B minus some y ("swap").
+// With the additive row hash H(A) = sum of g(col) mod 2^64 (g = splitmix64) every case is an equi-join:
+//     H(A) - g(x) = H(B), |B| = |A| - 1;     H(A) - g(x) - g(y) = H(B), |B| = |A| - 2;     H(A) - g(x) = H(B) - g(y), |A| = |B|.
+// A true edge always satisfies its join, so none is lost; every match goes through k_verify_unite (exact distance on the
+// rows), so a hash or tag collision cannot add one.  Tables: open addressing, one 64-bit word per entry
+// (tag = upper key half, row), linear probing; T1 = the rows (L2-resident at 10^6 rows), T2 = every one-deletion key
+// (swap join).  Same definition of an edge as the tile engines (breakfast.py:223-276 + sklearn _pairwise_fast.pyx:83-107);
+// no counterpart in the reference.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned long long HJ_EMPTY = ~0ull;
+constexpr int HJ_CBUF = 1024;   // candidates a block collects before one cursor update
+
+__device__ __forceinline__ unsigned long long hj_g(uint32_t col) {
+    unsigned long long x = (unsigned long long)col + 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long hj_mix(unsigned long long k) {   // slot hash: sums of g are uniform, but cheap insurance
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    return k ^ (k >> 29);
+}
+__device__ __forceinline__ void hj_insert(unsigned long long* __restrict__ table, unsigned long long mask, unsigned long long key, int row) {
+    const unsigned long long entry = (key & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)row;
+    unsigned long long slot = hj_mix(key) & mask;
+    while (atomicCAS(&table[slot], HJ_EMPTY, entry) != HJ_EMPTY) slot = (slot + 1) & mask;
+}
+
+// block-level candidate buffer: hits are rare (about one per hundred probes), a same-address atomic per hit would
+// serialise the whole kernel
+struct HjOut {
+    uint2* buf;              // shared, HJ_CBUF entries
+    unsigned* n;             // shared counter
+    uint2* cand;
+    unsigned long long cap;
+    unsigned long long* cursor;
+};
+__device__ __forceinline__ void hj_emit(const HjOut& o, int a, int b) {
+    const unsigned slot = atomicAdd(o.n, 1u);
+    if (slot < HJ_CBUF) {
+        o.buf[slot] = make_uint2((uint32_t)a, (uint32_t)b);
+    } else {
+        const unsigned long long pos = atomicAdd(o.cursor, 1ull);
+        if (pos < o.cap) o.cand[pos] = make_uint2((uint32_t)a, (uint32_t)b);
+    }
+}
+__device__ __forceinline__ void hj_flush(const HjOut& o, unsigned long long* base_s) {   // all threads of the block
+    __syncthreads();
+    const unsigned m = min(*o.n, (unsigned)HJ_CBUF);
+    if (threadIdx.x == 0 && m) *base_s = atomicAdd(o.cursor, (unsigned long long)m);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < m; i += blockDim.x)
+        if (*base_s + i < o.cap) o.cand[*base_s + i] = o.buf[i];
+}
+
+// H[r] and insertion into T1; eight lanes per row
+__global__ void __launch_bounds__(256) k_hj_hash_rows(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n,
+                                                      unsigned long long* __restrict__ H, unsigned long long* __restrict__ t1,
+                                                      unsigned long long mask1) {
+    const int sub = threadIdx.x & 7;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+    unsigned long long h = 0;
+    if (r < n) {
+        const int64_t b = __ldg(&indptr[r]), e = __ldg(&indptr[r + 1]);
+        for (int64_t k = b + sub; k < e; k += 8) h += hj_g((uint32_t)__ldg(&indices[k]));
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (sub == 0 && r < n) {
+        H[r] = h;
+        hj_insert(t1, mask1, h, (int)r);
+    }
+}
+
+// one-deletion keys of every row -> T2 (swap join): full 64-bit keys (a key cannot be recomputed from its row alone)
+// with the rows in a parallel array, written after the slot is claimed and read by a later kernel; eight lanes per row.
+// A key equal to HJ_EMPTY is stored as HJ_EMPTY - 1 (a collision like any other: matches are verified exactly).
+__device__ __forceinline__ unsigned long long hj_key2(unsigned long long key) { return key == HJ_EMPTY ? HJ_EMPTY - 1 : key; }
+__global__ void __launch_bounds__(256) k_hj_build_deletions(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n,
+                                                            const unsigned long long* __restrict__ H, unsigned long long* __restrict__ t2,
+                                                            int32_t* __restrict__ t2_rows, unsigned long long mask2) {
+    const int sub = threadIdx.x & 7;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+    if (r >= n) return;
+    const int64_t b = __ldg(&indptr[r]), e = __ldg(&indptr[r + 1]);
+    const unsigned long long h = __ldg(&H[r]);
+    for (int64_t k = b + sub; k < e; k += 8) {
+        const unsigned long long key = hj_key2(h - hj_g((uint32_t)__ldg(&indices[k])));
+        unsigned long long slot = hj_mix(key) & mask2;
+        while (atomicCAS(&t2[slot], HJ_EMPTY, key) != HJ_EMPTY) slot = (slot + 1) & mask2;
+        t2_rows[slot] = (int32_t)r;
+    }
+}
+
+// probes of the one-deletion keys: MODE 1 against T1 (distance 1: |B| = |A| - 1), MODE 2 against T2 (distance-2 swaps:
+// |B| = |A|, B > A so that a pair is reported once).  Row q of this rank is row q * world + rank; eight lanes per row.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_hj_probe_deletions(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n,
+                                                            const unsigned long long* __restrict__ H, const unsigned long long* __restrict__ table,
+                                                            const int32_t* __restrict__ t2_rows, unsigned long long mask, int rank, int world,
+                                                            const unsigned char* __restrict__ is_query, uint2* __restrict__ cand,
+                                                            unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    __shared__ uint2 cbuf[HJ_CBUF];
+    __shared__ unsigned cbuf_n;
+    __shared__ unsigned long long cbuf_base;
+    if (threadIdx.x == 0) cbuf_n = 0;
+    __syncthreads();
+    const HjOut out{cbuf, &cbuf_n, cand, cand_cap, &counters->n_cand};
+    const int sub = threadIdx.x & 7;
+    const int64_t r = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3) * world + rank;
+    if (r < n) {
+        const int64_t b = __ldg(&indptr[r]), e = __ldg(&indptr[r + 1]);
+        const int64_t want_len = MODE == 1 ? e - b - 1 : e - b;
+        const unsigned long long h = __ldg(&H[r]);
+        const bool a_is_q = is_query ? is_query[r] != 0 : true;
+        for (int64_t k = b + sub; k < e; k += 8) {
+            unsigned long long key = h - hj_g((uint32_t)__ldg(&indices[k]));
+            if (MODE == 2) key = hj_key2(key);
+            const unsigned long long tag = key & 0xffffffff00000000ull;
+            unsigned long long slot = hj_mix(key) & mask;
+            while (true) {
+                const unsigned long long ent = __ldg(&table[slot]);
+                if (ent == HJ_EMPTY) break;
+                if (MODE == 1) {
+                    if ((ent & 0xffffffff00000000ull) == tag) {   // T1: tag + row; the full key is the row's hash
+                        const int rb = (int)(uint32_t)ent;
+                        if (__ldg(&H[rb]) == key && __ldg(&indptr[rb + 1]) - __ldg(&indptr[rb]) == want_len && (a_is_q || is_query[rb]))
+                            hj_emit(out, (int)r, rb);
+                    }
+                } else if (ent == key) {                          // T2: full keys, rows beside them
+                    const int rb = __ldg(&t2_rows[slot]);
+                    // rows with equal hashes (identical rows, or a collision) are the business of k_hj_probe_equal
+                    if (rb > (int)r && __ldg(&H[rb]) != h && __ldg(&indptr[rb + 1]) - __ldg(&indptr[rb]) == want_len &&
+                        (a_is_q || is_query[rb]))
+                        hj_emit(out, (int)r, rb);
+                }
+                slot = (slot + 1) & mask;
+            }
+        }
+    }
+    hj_flush(out, &cbuf_base);
+}
+
+// distance-2 supersets: H(A) - g(x) - g(y) against T1 for every pair x < y of A's columns; a warp per row
+__global__ void __launch_bounds__(256) k_hj_probe_pairs(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n,
+                                                        const unsigned long long* __restrict__ H, const unsigned long long* __restrict__ t1,
+                                                        unsigned long long mask1, int rank, int world,
+                                                        const unsigned char* __restrict__ is_query, uint2* __restrict__ cand,
+                                                        unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    __shared__ uint2 cbuf[HJ_CBUF];
+    __shared__ unsigned cbuf_n;
+    __shared__ unsigned long long cbuf_base;
+    if (threadIdx.x == 0) cbuf_n = 0;
+    __syncthreads();
+    const HjOut out{cbuf, &cbuf_n, cand, cand_cap, &counters->n_cand};
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * world + rank;
+    if (r < n) {
+        const int64_t b = __ldg(&indptr[r]), e = __ldg(&indptr[r + 1]);
+        const int64_t want_len = e - b - 2;
+        const unsigned long long h = __ldg(&H[r]);
+        const bool a_is_q = is_query ? is_query[r] != 0 : true;
+        for (int64_t i = b; i + 1 < e; ++i) {
+            const unsigned long long hx = h - hj_g((uint32_t)__ldg(&indices[i]));
+            for (int64_t j = i + 1 + lane; j < e; j += 32) {
+                const unsigned long long key = hx - hj_g((uint32_t)__ldg(&indices[j]));
+                const unsigned long long tag = key & 0xffffffff00000000ull;
+                unsigned long long slot = hj_mix(key) & mask1;
+                while (true) {
+                    const unsigned long long ent = __ldg(&t1[slot]);
+                    if (ent == HJ_EMPTY) break;
+                    if ((ent & 0xffffffff00000000ull) == tag) {
+                        const int rb = (int)(uint32_t)ent;
+                        if (__ldg(&H[rb]) == key && __ldg(&indptr[rb + 1]) - __ldg(&indptr[rb]) == want_len && (a_is_q || is_query[rb]))
+                            hj_emit(out, (int)r, rb);
+                    }
+                    slot = (slot + 1) & mask1;
+                }
+            }
+        }
+    }
+    hj_flush(out, &cbuf_base);
+}
+
+// rows with equal hashes (identical rows; or, with probability 2^-64 per pair, different ones - the verify step decides):
+// every row looks its own hash up in T1 and reports the equal-length rows after it
+__global__ void __launch_bounds__(256) k_hj_probe_equal(const int64_t* __restrict__ indptr, int64_t n, const unsigned long long* __restrict__ H,
+                                                        const unsigned long long* __restrict__ t1, unsigned long long mask1, int rank,
+                                                        int world, const unsigned char* __restrict__ is_query, uint2* __restrict__ cand,
+                                                        unsigned long long cand_cap, DevCounters* __restrict__ counters) {
+    __shared__ uint2 cbuf[HJ_CBUF];
+    __shared__ unsigned cbuf_n;
+    __shared__ unsigned long long cbuf_base;
+    if (threadIdx.x == 0) cbuf_n = 0;
+    __syncthreads();
+    const HjOut out{cbuf, &cbuf_n, cand, cand_cap, &counters->n_cand};
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * world + rank;
+    if (r < n) {
+        const unsigned long long key = __ldg(&H[r]), tag = key & 0xffffffff00000000ull;
+        const int64_t len = __ldg(&indptr[r + 1]) - __ldg(&indptr[r]);
+        const bool a_is_q = is_query ? is_query[r] != 0 : true;
+        unsigned long long slot = hj_mix(key) & mask1;
+        while (true) {
+            const unsigned long long ent = __ldg(&t1[slot]);
+            if (ent == HJ_EMPTY) break;
+            if ((ent & 0xffffffff00000000ull) == tag) {
+                const int rb = (int)(uint32_t)ent;
+                if (rb > (int)r && __ldg(&H[rb]) == key && __ldg(&indptr[rb + 1]) - __ldg(&indptr[rb]) == len && (a_is_q || is_query[rb]))
+                    hj_emit(out, (int)r, rb);
+            }
+            slot = (slot + 1) & mask1;
+        }
+    }
+    hj_flush(out, &cbuf_base);
 }
 
 __global__ void k_mark_rows(const int32_t* __restrict__ rows, int64_t n, unsigned char* __restrict__ flags) {

@@ -35,6 +35,8 @@ def _context_options() -> dict:
     opts = {}
     if "BREAKFAST_B200_SKETCH_BITS" in os.environ:
         opts["sketch_bits"] = int(os.environ["BREAKFAST_B200_SKETCH_BITS"])
+    if "BREAKFAST_B200_MERGE_CAPACITY" in os.environ:   # entries per rank of the multi-GPU label exchange (tests)
+        opts["merge_capacity"] = int(os.environ["BREAKFAST_B200_MERGE_CAPACITY"])
     return opts
 
 

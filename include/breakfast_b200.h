@@ -53,8 +53,14 @@ typedef enum bf_status {
  *           on the CSR rows.  Exact.  Default.
  *   FULL:   all n_cols columns as dense bitsets, tiled XOR/POPC over the whole
  *           width, threshold is exact, no verify stage.  Exact.
+ *   HASHJOIN (max_dist <= 2 only, BF_ERR_INVALID beyond): no pair tiles at all.  Small distances have a closed
+ *           form (distance 1: one row is the other minus a column; distance 2: minus two columns, or equal size
+ *           and equal after deleting one column each), and with an additive 64-bit row hash each case is an
+ *           equi-join against a hash table of the rows / of their one-deletion keys; every match is verified
+ *           exactly on the CSR rows.  Exact.  O(nnz) probes at distance 1 instead of O(N^2 / pruning) pairs
+ *           (no counterpart in the reference).
  */
-typedef enum bf_engine { BF_ENGINE_SKETCH = 0, BF_ENGINE_FULL = 1 } bf_engine;
+typedef enum bf_engine { BF_ENGINE_SKETCH = 0, BF_ENGINE_FULL = 1, BF_ENGINE_HASHJOIN = 2 } bf_engine;
 
 typedef struct bf_stats {
     int64_t n_rows;           /* rows on the B side (all profiles)                     */
@@ -214,8 +220,9 @@ int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_
 int bf_pinned_alloc(int64_t bytes, void** ptr_out);
 void bf_pinned_free(void* ptr);
 /* Register-resident pipe microbenchmarks on `device`; result in 1e9 lane-ops/s.
- * name: "popc32", "lop3", "iadd3", "xor_popc_add", or "imma_s8" (mma.sync m16n8k32 int8, result in
- * 1e9 int8 MACs/s). Roofline denominators. */
+ * name: "popc32", "lop3", "iadd3", "xor_popc_add", "imma_s8" (mma.sync m16n8k32 int8, result in
+ * 1e9 int8 MACs/s) or "umma_i8" (tcgen05.mma kind::i8 M128 N256 K32 with TMEM accumulators, 1e9 int8 MACs/s).
+ * Roofline denominators. */
 int bf_measure_peak(int32_t device, const char* name, double* gops_out);
 
 #ifdef __cplusplus

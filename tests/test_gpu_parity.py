@@ -191,7 +191,7 @@ def test_schedule_counter_matches_the_cpu_mirror(max_dist):
         ctx.upload_csr(indptr, indices, n_cols)
         st = ctx.run_sync(max_dist)
     assert st.tiles_band == schedule_sim.tile_pairs(indptr, indices, max_dist, 3)
-    assert st.tiles_band < schedule_sim.tile_pairs(indptr, indices, max_dist, 2) < schedule_sim.tile_pairs(indptr, indices, max_dist, 1)
+    assert st.tiles_band <= schedule_sim.tile_pairs(indptr, indices, max_dist, 2) < schedule_sim.tile_pairs(indptr, indices, max_dist, 1)
 
 
 def _near_duplicate_rows(n, card, n_cols, seed, spread):
@@ -323,6 +323,32 @@ def test_single_process_multi_device_engine(monkeypatch, tmp_path):
                                                         "--gpus", "2"] + helpers.cli_args(case["opts"]))
     assert r.exit_code == 0, r.output
     helpers.assert_matches(case, case["expected"], (tmp_path / "clusters.tsv").read_text())
+
+
+@pytest.mark.parametrize("merge_capacity", [0, 64], ids=["auto", "tiny-exchange-buffer"])
+def test_in_library_communicator_on_distinct_devices(merge_capacity, monkeypatch):
+    """two (or four) real GPUs in one process: bf_comm_init_all gives the contexts the library's NCCL communicator, the
+    sketch pass is sharded and the union-finds are exchanged inside bf_run; labels and edges equal the single-GPU answer,
+    for the full run and for the incremental rectangle, with a deliberately small exchange capacity (overflow -> rerun)"""
+    from breakfast_b200 import engine
+    n_dev = _native.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    devices = list(range(4 if n_dev >= 4 else 2))
+    if merge_capacity:
+        monkeypatch.setenv("BREAKFAST_B200_MERGE_CAPACITY", str(merge_capacity))
+    indptr, indices, n_cols = synth.generate(30000, seed=17).csr()
+    want_labels, _ = oracle.cluster(indptr, indices, 2)
+    ws, wd = oracle.edges(indptr, indices, 2)
+    res = engine._components_multi_device(indptr, indices, n_cols, 2, devices, True, "sketch")
+    assert res.stats["label_merge"].startswith("nccl")
+    assert np.array_equal(res.labels, want_labels)
+    assert np.array_equal(res.edges[0], ws) and np.array_equal(res.edges[1], wd)
+    q = np.arange(0, 30000, 7, dtype=np.int32)
+    qs, qd = oracle.edges(indptr, indices, 1, queries=q)
+    res = engine._components_multi_device(indptr, indices, n_cols, 1, devices, True, "sketch", query_rows=q)
+    assert np.array_equal(res.edges[0], qs) and np.array_equal(res.edges[1], qd)
+    assert np.array_equal(res.labels, oracle.components(30000, qs, qd))
 
 
 def test_merge_on_device_with_torch_tensors():
@@ -457,6 +483,61 @@ def test_async_double_buffered_upload_and_adopted_device_csr():
             assert np.array_equal(ctx.download_labels(), wants[1])
 
 
+# ------------------------------------------------------------------ hash-join engine (max_dist <= 2)
+@pytest.mark.parametrize("max_dist", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 2, 129, 1000, 4097, 30000])
+def test_hashjoin_engine_matches_oracle(n, max_dist):
+    """the third engine (equi-joins on an additive row hash + exact verification): labels, edges and counters of oracle.c"""
+    indptr, indices, n_cols = synth.generate(n, seed=300 + n).csr()
+    want_labels, want_ne = oracle.cluster(indptr, indices, max_dist)
+    labels, st = _native.cluster_csr(indptr, indices, n_cols, max_dist, engine="hashjoin")
+    assert np.array_equal(labels, want_labels) and st.n_edges == want_ne
+    src, dst, st2 = _native.neighbours_csr(indptr, indices, n_cols, max_dist, engine="hashjoin")
+    ws, wd = oracle.edges(indptr, indices, max_dist)
+    assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+    _, st_sketch = _native.cluster_csr(indptr, indices, n_cols, max_dist, engine="sketch")
+    assert st.pairs_band == st_sketch.pairs_band and st.pairs_total == st_sketch.pairs_total
+
+
+def test_hashjoin_engine_identical_rows_rectangle_ranks_and_limits():
+    rows = [{1, 2, 3}, {1, 2, 3}, {1, 2}, {1, 2, 3, 9}, {5, 6, 7, 8}, {5, 6, 7, 9}, {5, 6}, set(), set(), {70000, 5, 6}]
+    indptr, indices, n_cols = rows_to_csr(rows, 70001)
+    for d in (0, 1, 2):
+        want, _ = oracle.cluster(indptr, indices, d)
+        got, _ = _native.cluster_csr(indptr, indices, n_cols, d, engine="hashjoin")
+        assert np.array_equal(got, want), d
+        ws, wd = oracle.edges(indptr, indices, d)
+        src, dst, _ = _native.neighbours_csr(indptr, indices, n_cols, d, engine="hashjoin")
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd), d
+    with pytest.raises(_native.NativeError):
+        _native.cluster_csr(indptr, indices, n_cols, 3, engine="hashjoin")
+    # rectangle (incremental path): pairs with at least one endpoint among the query rows
+    indptr, indices, n_cols = synth.generate(20000, seed=31).csr()
+    q = np.arange(3, 20000, 11, dtype=np.int32)
+    for d in (1, 2):
+        ws, wd = oracle.edges(indptr, indices, d, queries=q)
+        src, dst, _ = _native.neighbours_csr(indptr, indices, n_cols, d, query_rows=q, engine="hashjoin")
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+    # three ranks (emulated one after the other): the probes are dealt by row, the merged labels are the single-rank ones
+    want, _ = oracle.cluster(indptr, indices, 2)
+    gathered = np.empty((3, 20000), dtype=np.int32)
+    edges = 0
+    with _native.Context(engine="hashjoin") as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        for r in range(3):
+            edges += ctx.run_sync(2, rank=r, world=3).n_edges
+            gathered[r] = ctx.download_labels()
+        ctx.merge_labels_host(gathered)
+        assert np.array_equal(ctx.download_labels(), want)
+    assert edges == oracle.edges(indptr, indices, 2)[0].size
+
+
+@pytest.mark.parametrize("case", [c for c in helpers.cases("plain") if c["opts"].get("max_dist", 1) in (1, 2)], ids=lambda c: c["name"])
+def test_cli_goldens_with_the_hashjoin_engine(case, tmp_path, monkeypatch):
+    monkeypatch.setenv("BREAKFAST_B200_ENGINE", "hashjoin")
+    helpers.assert_matches(case, case["expected"], helpers.run_cli(case["input"], case["opts"], tmp_path))
+
+
 def _pinned_copy(lib, arr):
     q = C.c_void_p()
     assert lib.bf_pinned_alloc(max(arr.nbytes, 1), C.byref(q)) == 0
@@ -510,6 +591,9 @@ def test_compact_csr16_upload_gives_the_plain_answer(wide):
 def test_measured_pipe_peaks_are_plausible():
     assert _native.measure_peak("popc32") > 1000.0
     assert _native.measure_peak("lop3") > _native.measure_peak("popc32")
+    # int8 tensor rates: tcgen05.mma kind::i8 (TMEM accumulators) is about four times mma.sync m16n8k32
+    imma, umma = _native.measure_peak("imma_s8"), _native.measure_peak("umma_i8")
+    assert imma > 1e5 and 2.5 * imma < umma < 6 * imma, (imma, umma)
 
 
 # ------------------------------------------------------------------ scale goldens (reference run on 42 k / 67 k sequences)
