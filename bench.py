@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
-    ap.add_argument("--engine", default="sketch", choices=["sketch", "full"])
+    ap.add_argument("--engine", default="sketch", choices=["sketch", "full", "hashjoin"])
     ap.add_argument("--two-level", type=int, default=1, choices=[0, 1])
     ap.add_argument("--level1", type=int, default=1, choices=[0, 1], help="1 = int8 mma.sync level 1 (default), 0 = integer pipes")
     ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
@@ -335,12 +335,13 @@ def main():
     ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits,
                           two_level=args.two_level, level1=args.level1)
     ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
-    runner = RankRunner(ctx, n, rank, world)
+    runner = RankRunner(ctx, n, rank, world)   # N > 1: joins the library's own NCCL communicator (NCCL may print its banner on stdout)
 
     # ---- device-resident leg: `value`
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    runner.run_sync(MAX_DIST)        # settles the bounded buffers (an overflow on any rank reruns every rank)
     for _ in range(args.warmup):
         runner.step(MAX_DIST)
     st = ctx.sync()
@@ -402,6 +403,16 @@ def main():
         ops_per_launch = int(st.pairs_evaluated * (alu_per_pair if bound == "int_pipe_alu" else popc_per_pair))
         extra = {"alu_frac": alu_frac, "xu_frac": xu_frac, "alu_ops_per_pair": alu_per_pair, "popc_per_pair": popc_per_pair,
                  "level2_units": st.l2_warp_items, "ms_level2": (st.ms_pairs_sum - st.ms_l1_sum) / runs}
+    elif args.engine == "hashjoin":
+        # the probes of the hash-join engine: nnz (distance 1) random 8-byte reads of an L2-resident table; algorithmic
+        # traffic = one 32-byte sector per probe, reported against the HBM peak for want of a measured L2 figure
+        ms_kernel = ms_pairs
+        kernel_name = "k_hj_probe_deletions<1> (one probe per stored column against the row table)"
+        hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+        bound, unit_r, peak = "hbm", "GB/s (32-byte sector per probe; the table is L2-resident)", hbm
+        ops_per_launch = int(indices.size // world) * 32
+        achieved = ops_per_launch / (ms_kernel * 1e-3) / 1e9
+        extra = {"probes_per_launch": int(indices.size // world)}
     else:
         ms_kernel = ms_pairs
         kernel_name = f"k_pairs<K4> ({args.engine}, {st.bits_per_row} bits/row)"

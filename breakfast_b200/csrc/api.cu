@@ -164,6 +164,7 @@ struct bf_ctx {
     bfnccl::comm_t comm = nullptr;
     int comm_rank = 0, comm_world = 1;
     int64_t merge_capacity = 0;   // entries per rank of the compact label exchange, 0 = automatic
+    int64_t merge_auto = 0;       // automatic capacity learnt from earlier passes (what the fullest list needed, + 25 %)
     unsigned long long merge_cap_used = 0;
     DevBuf xchg;
 
@@ -346,8 +347,10 @@ int exchange_labels(bf_ctx* c) {
     const int64_t n = c->n_rows;
     if (n == 0) return BF_OK;
     bfnccl::Api& nc = bfnccl::api();
+    // a rank's list has about (edges / world) entries; first guess 1.25 N / world, afterwards what the data needed
     const unsigned long long cap = c->merge_capacity > 0 ? (unsigned long long)c->merge_capacity
-                                                         : (unsigned long long)std::max<int64_t>(4096, n / 8);
+                                   : c->merge_auto > 0   ? (unsigned long long)c->merge_auto
+                                                         : (unsigned long long)std::max<int64_t>(4096, n / c->world + n / (4 * c->world));
     c->merge_cap_used = cap;
     const size_t words_rank = (size_t)cap + 1;
     TRY(c->xchg.ensure(words_rank * c->world * sizeof(unsigned long long)));
@@ -1322,10 +1325,13 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
             }
             c->sort_slots = std::min<int>(SORT_MAX_SLOTS, (int)h.sort_passes);   // exactly what this data needs from now on
         }
-        if (dist_run(c) && h.merge_fullest > c->merge_cap_used) {
-            c->merge_capacity = (int64_t)h.merge_fullest + h.merge_fullest / 4 + 1024;
-            snprintf(buf, sizeof buf, "label exchange: %u entries > capacity %llu; ", h.merge_fullest, c->merge_cap_used);
-            what += buf;
+        if (dist_run(c) && c->n_rows > 0) {
+            if (h.merge_fullest > c->merge_cap_used) {
+                snprintf(buf, sizeof buf, "label exchange: %u entries > capacity %llu; ", h.merge_fullest, c->merge_cap_used);
+                what += buf;
+                if (c->merge_capacity > 0) c->merge_capacity = (int64_t)h.merge_fullest + h.merge_fullest / 4 + 1024;
+            }
+            c->merge_auto = (int64_t)h.merge_fullest + h.merge_fullest / 4 + 1024;   // every rank sees every count: same value everywhere
         }
         if (c->ran_two_kernel && c->n_query > 0 && c->n_rows > 0) {
             if (nwork > c->items_cap_used) {
