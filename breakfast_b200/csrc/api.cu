@@ -197,8 +197,11 @@ struct bf_ctx {
     cudaEvent_t ev_upload_done = nullptr, ev_upload_start = nullptr, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
     DevBuf keysB[3], valsB[3], keysA[3], valsA[3], sort_counts, sort_max, sk_rows, sched_table;
-    int sort_slots = bf::SORT_MAX_SLOTS;   // radix pass slots launched per sort; lowered to what the data needs after a sync
     int sched_table_dist = -1, sched_table_n = 0;
+    // the candidate-pair statistic (pairs_band) depends on the rows and max_dist only: counted once per uploaded matrix
+    DevBuf band_cache;
+    bool band_valid = false;
+    int band_dist = -1;
     DevBuf bitsA, bitsB, foldsA[2], foldsB[2], fold8A[2], fold8B[2], jlo, jend, wprefix, nwork, items, queue, segcnt, cand, edges, parent, labels, counters, scratch, scratch2;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_aux[2] = {};
@@ -223,8 +226,6 @@ int set_device(bf_ctx* c) {
 // keys_ready: keys[0] / vals[0] and the OR word of `side` were already written (k_pack_sketch_rows, k_gather_keys).
 int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[3], DevBuf vals[3], int side, bool keys_ready) {
     if (n == 0) return BF_OK;
-    const int nblocks = (int)ceil_div(n, SORT_ITEMS);
-    TRY(c->sort_counts.ensure((size_t)256 * (nblocks + 1) * sizeof(uint32_t)));
     sortkey_t* or_key = c->sort_max.as<sortkey_t>() + side;
     if (!keys_ready) {
         CK(cudaMemsetAsync(or_key, 0, sizeof(sortkey_t), c->stream));
@@ -237,16 +238,14 @@ int sort_by_card(bf_ctx* c, const int32_t* rows_dev, int64_t n, DevBuf keys[3], 
         b.k[i] = keys[i].as<sortkey_t>();
         b.v[i] = vals[i].as<int32_t>();
     }
-    unsigned int* needed = &c->counters.as<DevCounters>()->sort_passes;
-    uint32_t* totals = c->sort_counts.as<uint32_t>() + (size_t)256 * nblocks;
-    for (int pass = 0; pass < c->sort_slots; ++pass) {
-        k_sort_hist<<<nblocks, 256, 0, c->stream>>>(b, n, pass, c->sort_counts.as<uint32_t>(), nblocks, or_key, needed);
-        CKLC(c);
-        k_sort_scan_digits<<<256 / 8, 256, 0, c->stream>>>(c->sort_counts.as<uint32_t>(), nblocks, totals, pass, or_key);
-        CKLC(c);
-        k_sort_scatter<<<nblocks, 256, 0, c->stream>>>(b, n, pass, c->sort_counts.as<uint32_t>(), totals, nblocks, or_key);
-        CKLC(c);
-    }
+    // one cooperative launch: a block per SM, all passes inside (grid-wide barriers between the phases)
+    const int grid = c->num_sms;
+    TRY(c->sort_counts.ensure((size_t)256 * grid * sizeof(uint32_t)));
+    uint32_t* counts = c->sort_counts.as<uint32_t>();
+    int64_t n_arg = n;
+    void* args[] = {&b, &n_arg, &counts, &or_key};
+    CK(cudaLaunchCooperativeKernel((const void*)k_radix_sort, dim3((unsigned)grid), dim3(SORT_THREADS), args, 0, c->stream));
+    CKLC(c);
     return BF_OK;
 }
 
@@ -497,6 +496,27 @@ int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int
     return BF_OK;
 }
 
+// candidate pairs of the metric (||A| - |B|| <= max_dist): a statistic of the uploaded matrix, not of a pass - counted by
+// the first pass after an upload and restored from a 16-byte device cache by the following ones
+int band_statistic(bf_ctx* c, const sortkey_t* keysA, int64_t nA, const sortkey_t* keysB, int64_t nB, int max_dist) {
+    DevCounters* dc = c->counters.as<DevCounters>();
+    TRY(c->band_cache.ensure(2 * sizeof(unsigned long long)));
+    if (c->band_valid && c->band_dist == max_dist) {
+        CK(cudaMemcpyAsync(&dc->band_ab, c->band_cache.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+        return BF_OK;
+    }
+    k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA, nA, keysB, nB, max_dist, &dc->band_ab);
+    CKLC(c);
+    if (c->has_query) {
+        k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA, nA, keysA, nA, max_dist, &dc->band_aa);
+        CKLC(c);
+    }
+    CK(cudaMemcpyAsync(c->band_cache.p, &dc->band_ab, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    c->band_valid = true;
+    c->band_dist = max_dist;
+    return BF_OK;
+}
+
 inline unsigned long long hj_capacity(int64_t want) {
     unsigned long long cap = 1024;
     while ((int64_t)cap < want) cap <<= 1;
@@ -634,7 +654,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query,
                       &c->hj_hash, &c->hj_t1, &c->hj_t2, &c->hj_t2_rows, &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->keysB[0], &c->keysB[1], &c->keysB[2],
                       &c->valsB[0], &c->valsB[1], &c->valsB[2], &c->keysA[0], &c->keysA[1], &c->keysA[2], &c->valsA[0], &c->valsA[1], &c->valsA[2], &c->sched_table,
-                      &c->sort_counts, &c->sort_max, &c->sk_rows, &c->xchg, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
+                      &c->sort_counts, &c->sort_max, &c->sk_rows, &c->xchg, &c->band_cache, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -750,6 +770,7 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
     c->n_cols = n_cols;
     c->nnz = nnz;
     c->uploaded = true;
+    c->band_valid = false;
     return BF_OK;
 }
 
@@ -777,6 +798,7 @@ int bf_upload_csr_async(bf_ctx* c, const int64_t* indptr, const int32_t* indices
     c->pend_cols = n_cols;
     c->pend_nnz = nnz;
     c->uploaded = true;
+    c->band_valid = false;
     return BF_OK;
 }
 
@@ -850,6 +872,7 @@ int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* s
     c->pend_cols = n_cols;
     c->pend_nnz = nnz;
     c->uploaded = true;
+    c->band_valid = false;
     return BF_OK;
 }
 
@@ -866,6 +889,7 @@ int bf_adopt_csr_device(bf_ctx* c, const void* indptr_device, const void* indice
     c->nnz = nnz;
     c->has_query = false;
     c->uploaded = true;
+    c->band_valid = false;
     c->ran = false;
     c->ms_h2d = 0;
     return BF_OK;
@@ -944,13 +968,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         if (hashjoin) {   // rows are only sorted by cardinality here, for the candidate-pair statistic of the metric
             TRY(sort_by_card(c, nullptr, nB, c->keysB, c->valsB, 0, false));
             if (c->has_query) TRY(sort_by_card(c, c->query_rows.as<int32_t>(), nA, c->keysA, c->valsA, 1, false));
-            DevCounters* dc = c->counters.as<DevCounters>();
-            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, &dc->band_ab);
-            CKLC(c);
-            if (c->has_query) {
-                k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, keysA[0].as<sortkey_t>(), nA, max_dist, &dc->band_aa);
-                CKLC(c);
-            }
+            TRY(band_statistic(c, keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist));
         } else if (staged) {
             TRY(pack_stage_all_rows(c));
             if (c->has_query) {   // before the sort of the B side reuses keysB[0]
@@ -1017,13 +1035,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
         k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
         CKLC(c);
-        DevCounters* dc = c->counters.as<DevCounters>();
-        k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, &dc->band_ab);
-        CKLC(c);
-        if (c->has_query) {
-            k_band_count<<<grid_for(nA, 256), 256, 0, c->stream>>>(keysA[0].as<sortkey_t>(), nA, keysA[0].as<sortkey_t>(), nA, max_dist, &dc->band_aa);
-            CKLC(c);
-        }
+        TRY(band_statistic(c, keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist));
         // explicit work list for the producer (bounded; items beyond it fall back to a binary search)
         {
             const unsigned long long worst = c->has_query ? (unsigned long long)c->tilesA * c->tilesB
@@ -1318,13 +1330,6 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
     {
         std::string what;
         char buf[200];
-        if (c->n_query > 0 && c->n_rows > 0 && h.sort_passes > 0) {
-            if ((int)h.sort_passes > c->sort_slots) {
-                snprintf(buf, sizeof buf, "radix sort: %u passes > %d launched; ", h.sort_passes, c->sort_slots);
-                what += buf;
-            }
-            c->sort_slots = std::min<int>(SORT_MAX_SLOTS, (int)h.sort_passes);   // exactly what this data needs from now on
-        }
         if (dist_run(c) && c->n_rows > 0) {
             if (h.merge_fullest > c->merge_cap_used) {
                 snprintf(buf, sizeof buf, "label exchange: %u entries > capacity %llu; ", h.merge_fullest, c->merge_cap_used);
@@ -1505,6 +1510,7 @@ int bf_components(int64_t n_rows, const int32_t* src, const int32_t* dst, int64_
     auto body = [&]() -> int {
         c->n_rows = n_rows;
         c->uploaded = true;
+    c->band_valid = false;
         TRY(c->parent.ensure((size_t)std::max<int64_t>(n_rows, 1) * sizeof(int)));
         TRY(c->labels.ensure((size_t)std::max<int64_t>(n_rows, 1) * sizeof(int32_t)));
         CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));

@@ -27,13 +27,13 @@
 // conflict-free 128-bit shared loads.
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace bf {
 
 constexpr int TILE = 128;              // rows per tile (both operands)
 constexpr uint32_t KEY_CLAMP = 65535;  // cardinality sort key is clamped (1-Lipschitz, band test stays sound)
-constexpr int SORT_ITEMS = 2048;       // rows per block in the radix passes
 constexpr int PAIR_CONSUMER_WARPS = 16;
 constexpr int PAIR_THREADS = (PAIR_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 
@@ -48,7 +48,6 @@ struct DevCounters {
     unsigned long long n_units;        // level-2 queue cursor (may exceed capacity -> overflow)
     unsigned int n_comp;
     unsigned int seg_max;              // fullest per-CTA segment of the level-2 pair queue (overflow check)
-    unsigned int sort_passes;          // radix pass slots the keys of this run need (max over the sorted sides)
     unsigned int merge_fullest;        // longest compact label list of any rank in the exchange step (overflow check)
 };
 
@@ -107,11 +106,9 @@ __global__ void k_gather_keys(const sortkey_t* __restrict__ row_keys, const int3
 }
 
 // The sort runs over the COMPRESSED key: the bits that are set in at least one key (or_key), eight per pass, so real
-// data (cardinalities below 256, half cardinalities below 128: about 22 bits) needs three passes instead of six.
-// The host launches `slots` pass slots; slot p is real pass p if p < R = ceil(popc(or_key) / 8) and returns at once
-// otherwise (the host learns R at the next bf_sync and launches exactly R slots from then on; too few slots are an
-// overflow like any other and the pass is run again).  Three buffers make the result land in buffer 0 for any R:
-//   R even: 0 -> 1 -> 0 ...      R odd >= 3: 0 -> 2 -> 1 -> 0 -> 1 -> 0 ...      R = 1: 0 -> 1, slot 1 copies 1 -> 0.
+// data (cardinalities below 256, half cardinalities below 128: about 22 bits) needs three passes instead of six;
+// R = ceil(popc(or_key) / 8) is decided on the device.  Three buffers make the result land in buffer 0 for any R:
+//   R even: 0 -> 1 -> 0 ...      R odd >= 3: 0 -> 2 -> 1 -> 0 -> 1 -> 0 ...      R = 1: 0 -> 1, then a copy 1 -> 0.
 struct SortBufs {
     sortkey_t* k[3];
     int32_t* v[3];
@@ -121,10 +118,6 @@ struct SortPlan {
     int in, out;
     uint32_t pos[8];   // bit positions of this pass's digit bits (unused ones point at bit 63, which no key has)
 };
-__device__ __forceinline__ int sort_passes_needed(sortkey_t or_key) {
-    const int R = (__popcll(or_key) + 7) >> 3;
-    return R == 1 ? 2 : R;
-}
 __device__ __forceinline__ SortPlan sort_plan(sortkey_t or_key, int p) {
     SortPlan pl;
     const int R = (__popcll(or_key) + 7) >> 3;
@@ -151,141 +144,121 @@ __device__ __forceinline__ uint32_t sort_digit(sortkey_t key, const uint32_t (&p
     return d;
 }
 
-// One radix pass = k_sort_hist -> k_sort_scan_digits -> k_sort_scatter.  A block owns SORT_ITEMS
-// consecutive rows, warp w of it the w-th eighth; every warp keeps a private 256-bin histogram in
-// shared memory (no atomics: __match_any_sync groups equal digits, the group leader adds the group
-// size), so ranks are reproducible and the pass is stable.
-// counts[digit * nblocks + block] = number of rows of `block` whose digit == digit
-constexpr int SORT_WARPS = 8;
-constexpr int SORT_PER_WARP = SORT_ITEMS / SORT_WARPS;
-constexpr int SORT_MAX_SLOTS = 6;   // 48 key bits
+// The whole sort is ONE cooperative kernel (k_radix_sort): a persistent grid of one 1024-thread block per SM, a block
+// owns a contiguous slice of the rows, a warp a contiguous part of that slice.  Per pass: (1) every warp counts its
+// digits into a private 256-bin histogram in shared memory (no atomics: __match_any_sync groups equal digits, the group
+// leader adds the group size - reproducible ranks, stable pass); the block writes its 256 counts; grid-wide barrier;
+// (2) every block turns the counts of all blocks into its own digit offsets (256 threads, one digit each), the warps
+// re-read their keys and scatter; grid-wide barrier.  1 M rows: about 10 us per pass instead of three launches and
+// 36 us (round 1).  counts[block * 256 + digit].
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
 
-__device__ __forceinline__ void sort_warp_count(const sortkey_t* __restrict__ keys, int64_t n, const uint32_t (&pos)[8], int64_t wbase,
-                                                uint32_t* __restrict__ whist, int lane) {
-    for (int r = 0; r < SORT_PER_WARP; r += 32) {
-        const int64_t i = wbase + r + lane;
-        const bool valid = i < n;
-        const uint32_t d = valid ? sort_digit(keys[i], pos) : 256u + lane;  // invalid lanes match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[d] += __popc(peers);
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(256) k_sort_hist(SortBufs b, int64_t n, int p, uint32_t* __restrict__ counts, int nblocks,
-                                                   const sortkey_t* __restrict__ or_key, unsigned int* __restrict__ passes_needed) {
+__global__ void __launch_bounds__(SORT_THREADS, 1) k_radix_sort(SortBufs b, int64_t n, uint32_t* __restrict__ counts,
+                                                                const sortkey_t* __restrict__ or_key) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t whist[SORT_WARPS][256];
+    __shared__ uint32_t part_total[4][256], part_before[4][256];
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = gridDim.x, blk = blockIdx.x;
     const sortkey_t ok = *or_key;
-    if (p == 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(passes_needed, (unsigned int)sort_passes_needed(ok));
-    const SortPlan pl = sort_plan(ok, p);
-    if (!pl.active || pl.copy_only) return;
-    __shared__ uint32_t whist[SORT_WARPS][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
-    __syncthreads();
-    sort_warp_count(b.k[pl.in], n, pl.pos, (int64_t)blockIdx.x * SORT_ITEMS + warp * SORT_PER_WARP, whist[warp], lane);
-    __syncthreads();
-    uint32_t c = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) c += whist[w][threadIdx.x];
-    counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = c;
-}
-
-// Scan step of a radix pass: one warp per digit turns its row of counts[digit][block] into exclusive prefixes
-// over the blocks (in place) and leaves the digit's total in totals[digit]; k_sort_scatter adds the exclusive
-// scan over the 256 digit totals itself.
-__global__ void __launch_bounds__(256) k_sort_scan_digits(uint32_t* __restrict__ counts, int nblocks,
-                                                          uint32_t* __restrict__ totals, int p,
-                                                          const sortkey_t* __restrict__ or_key) {
-    const int R = (__popcll(*or_key) + 7) >> 3;
-    if (p >= R) return;
-    const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t* row = counts + (size_t)d * nblocks;
-    uint32_t carry = 0;
-    for (int b0 = 0; b0 < nblocks; b0 += 32) {
-        const int b = b0 + lane;
-        const uint32_t v = b < nblocks ? row[b] : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+    const int R = (__popcll(ok) + 7) >> 3;
+    const int n_slots = R == 1 ? 2 : R;
+    // slices: 32-aligned, so that a warp's 32-row steps never straddle two warps' parts
+    const int64_t per_block = ((n + G - 1) / G + 31) & ~(int64_t)31;
+    const int64_t b0 = min(n, per_block * blk), b1 = min(n, b0 + per_block);
+    const int64_t per_warp = (((b1 - b0) + SORT_WARPS - 1) / SORT_WARPS + 31) & ~(int64_t)31;
+    const int64_t w0 = min(b1, b0 + per_warp * warp), w1 = min(b1, w0 + per_warp);
+    for (int p = 0; p < n_slots; ++p) {
+        const SortPlan pl = sort_plan(ok, p);
+        const sortkey_t* __restrict__ keys = b.k[pl.in];
+        const int32_t* __restrict__ vals = b.v[pl.in];
+        sortkey_t* __restrict__ keys_out = b.k[pl.out];
+        int32_t* __restrict__ vals_out = b.v[pl.out];
+        if (pl.copy_only) {   // a single real pass left the result in buffer 1
+            for (int64_t i = b0 + threadIdx.x; i < b1; i += SORT_THREADS) {
+                keys_out[i] = keys[i];
+                vals_out[i] = vals[i];
+            }
+            break;
         }
-        if (b < nblocks) row[b] = carry + x - v;
-        carry += __shfl_sync(0xffffffffu, x, 31);
-    }
-    if (lane == 0) totals[d] = carry;
-}
-
-__global__ void __launch_bounds__(256) k_sort_scatter(SortBufs b, int64_t n, int p,
-                                                      const uint32_t* __restrict__ offsets,
-                                                      const uint32_t* __restrict__ totals, int nblocks,
-                                                      const sortkey_t* __restrict__ or_key) {
-    const SortPlan pl = sort_plan(*or_key, p);
-    if (!pl.active) return;
-    const sortkey_t* __restrict__ keys = b.k[pl.in];
-    const int32_t* __restrict__ vals = b.v[pl.in];
-    sortkey_t* __restrict__ keys_out = b.k[pl.out];
-    int32_t* __restrict__ vals_out = b.v[pl.out];
-    const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS;
-    if (pl.copy_only) {  // a single real pass left the result in buffer 1
-        const int m = (int)min((int64_t)SORT_ITEMS, n - base);
-        for (int i = threadIdx.x; i < m; i += 256) {
-            keys_out[base + i] = keys[base + i];
-            vals_out[base + i] = vals[base + i];
-        }
-        return;
-    }
-    __shared__ uint32_t whist[SORT_WARPS][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += 256) (&whist[0][0])[i] = 0;
-    __syncthreads();
-    const int64_t wbase = base + warp * SORT_PER_WARP;
-    sort_warp_count(keys, n, pl.pos, wbase, whist[warp], lane);
-    __syncthreads();
-    __shared__ uint32_t wsum[SORT_WARPS];
-    uint32_t digit_base;   // exclusive scan over the 256 digit totals (thread = digit)
-    {
-        const uint32_t t = totals[threadIdx.x];
-        uint32_t x = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) wsum[warp] = x;
+        for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
         __syncthreads();
-        uint32_t before = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) before += w < warp ? wsum[w] : 0u;
-        digit_base = before + x - t;
-    }
-    {   // digit d: global start of the block + exclusive prefix over the warps of the block
-        uint32_t run = digit_base + offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            const uint32_t c = whist[w][threadIdx.x];
-            whist[w][threadIdx.x] = run;
-            run += c;
+        for (int64_t i0 = w0; i0 < w1; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool valid = i < w1;
+            const uint32_t d = valid ? sort_digit(keys[i], pl.pos) : 256u + lane;  // invalid lanes match nobody
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[warp][d] += __popc(peers);
+            __syncwarp();
         }
-    }
-    __syncthreads();
-    uint32_t* wpos = whist[warp];
-    for (int r = 0; r < SORT_PER_WARP; r += 32) {
-        const int64_t i = wbase + r + lane;
-        const bool valid = i < n;
-        const sortkey_t k = valid ? keys[i] : 0ull;
-        const uint32_t d = valid ? sort_digit(k, pl.pos) : 256u + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned below = peers & ((1u << lane) - 1u);
-        uint32_t pos = 0;
-        if (valid) pos = wpos[d] + __popc(below);
-        __syncwarp();
-        if (valid && below == 0) wpos[d] += __popc(peers);
-        __syncwarp();
-        if (valid) {
-            keys_out[pos] = k;
-            vals_out[pos] = vals[i];
+        __syncthreads();
+        if (threadIdx.x < 256) {   // digit = threadIdx.x: exclusive prefix over the warps, the block's count to global memory
+            uint32_t run = 0;
+#pragma unroll 8
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                const uint32_t c = whist[w][threadIdx.x];
+                whist[w][threadIdx.x] = run;
+                run += c;
+            }
+            counts[(size_t)blk * 256 + threadIdx.x] = run;
         }
+        __threadfence();
+        grid.sync();
+        {   // rows of every digit in earlier blocks and in all blocks: four threads per digit, loads coalesced over the digits
+            const int q = threadIdx.x >> 8, d = threadIdx.x & 255;
+            uint32_t before = 0, total = 0;
+#pragma unroll 8
+            for (int g = q; g < G; g += 4) {
+                const uint32_t c = __ldcg(&counts[(size_t)g * 256 + d]);
+                total += c;
+                before += g < blk ? c : 0u;
+            }
+            part_total[q][d] = total;
+            part_before[q][d] = before;
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const uint32_t total = part_total[0][threadIdx.x] + part_total[1][threadIdx.x] + part_total[2][threadIdx.x] + part_total[3][threadIdx.x];
+            const uint32_t before = part_before[0][threadIdx.x] + part_before[1][threadIdx.x] + part_before[2][threadIdx.x] + part_before[3][threadIdx.x];
+            // exclusive scan of the digit totals over the 256 digits (8 warps)
+            uint32_t x = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) wsum[warp] = x;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint32_t base = x - total + before;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) base += w < warp ? wsum[w] : 0u;
+#pragma unroll 8
+            for (int w = 0; w < SORT_WARPS; ++w) whist[w][threadIdx.x] += base;
+        }
+        __syncthreads();
+        uint32_t* wpos = whist[warp];
+        for (int64_t i0 = w0; i0 < w1; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool valid = i < w1;
+            const sortkey_t k = valid ? keys[i] : 0ull;
+            const uint32_t d = valid ? sort_digit(k, pl.pos) : 256u + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned below = peers & ((1u << lane) - 1u);
+            uint32_t pos = 0;
+            if (valid) pos = wpos[d] + __popc(below);
+            __syncwarp();
+            if (valid && below == 0) wpos[d] += __popc(peers);
+            __syncwarp();
+            if (valid) {
+                keys_out[pos] = k;
+                vals_out[pos] = vals[i];
+            }
+        }
+        __threadfence();
+        grid.sync();
     }
 }
 
