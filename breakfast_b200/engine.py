@@ -94,6 +94,10 @@ def binary_csr(features, sep: str):
     return thermometer_binarise(indptr, indices, len(vocab))
 
 
+# seconds the last single-device engine call spent in each step (context, H2D, pass, D2H, teardown) - for benchmarks
+LAST_TIMINGS: dict = {}
+
+
 @dataclass
 class ClusterResult:
     labels: np.ndarray                       # int32 [n]: smallest row index of the row's component
@@ -191,11 +195,19 @@ def components_full(indptr, indices, n_cols, max_dist, want_edges=False, device=
     if device is None and len(default_devices()) > 1:
         return _components_multi_device(indptr, indices, n_cols, max_dist, default_devices(), want_edges, engine)
     device = default_device() if device is None else device
+    import time
+    t0 = time.perf_counter()
     with _native.Context(device=device, engine=engine, want_edges=int(bool(want_edges)), **_context_options()) as ctx:
+        t1 = time.perf_counter()
         ctx.upload_csr(indptr, indices, n_cols)
+        t2 = time.perf_counter()
         st = ctx.run_sync(max_dist)
+        t3 = time.perf_counter()
         labels = ctx.download_labels()
         edges = ctx.download_edges() if want_edges else None
+        t4 = time.perf_counter()
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update(context=t1 - t0, upload=t2 - t1, run=t3 - t2, download=t4 - t3, teardown=time.perf_counter() - t4)
     return ClusterResult(labels, st.as_dict(), edges)
 
 

@@ -9,6 +9,7 @@ expressions as filter_features.  tests/test_host_cpu.py checks both paths agains
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -26,6 +27,8 @@ def _load():
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         lib.bfh_tokenise.restype = vp
         lib.bfh_tokenise.argtypes = [C.c_char_p, i64, C.c_char, C.c_char_p, i32, i64]
+        lib.bfh_tokenise_arrow.restype = vp
+        lib.bfh_tokenise_arrow.argtypes = [vp, vp, i32, i64, C.c_char_p, i32, i32]
         for name in ("bfh_n_tokens", "bfh_distinct_bytes", "bfh_n_unique", "bfh_n_invalid", "bfh_token_nnz",
                      "bfh_binary_nnz", "bfh_string_bytes"):
             getattr(lib, name).restype = i64
@@ -61,28 +64,52 @@ def available() -> bool:
     return True
 
 
-def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length):
+def host_threads() -> int:
+    """threads for the native host pass: BREAKFAST_B200_HOST_THREADS, else min(cores, 16)"""
+    env = os.environ.get("BREAKFAST_B200_HOST_THREADS", "")
+    if env.strip():
+        return max(1, int(env))
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
+def _arrow_strings(series):
+    """(arrow array, data pointer, offsets pointer, offset width) of a pandas string column, or None when the column
+    holds missing values or cannot be viewed as one contiguous Arrow string array"""
+    import pyarrow as pa
+    try:
+        arr = pa.array(series)
+    except (pa.ArrowInvalid, pa.ArrowTypeError, TypeError):
+        return None
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks()
+    if arr.null_count or not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+        return None
+    width = 8 if pa.types.is_large_string(arr.type) else 4
+    _, offsets, data = arr.buffers()
+    return arr, (data.address if data is not None else 0), offsets.address + arr.offset * width, width
+
+
+def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length, threads=None):
     """meta (DataFrame[id, feature], raw profiles) -> (meta_nodups, csr): meta_nodups exactly as
     collapse_duplicates(meta with feature = filter_features(...)) would build it, csr = the token CSR and the
     binary CSR of the unique profiles (a plain dict handed to breakfast.cluster(..., pre=csr); it is NOT stored
     in DataFrame.attrs, which pandas deep-copies on every column access and pickles into the cache).  Returns
-    None when the input cannot take the fast path (a profile containing NUL); the caller then uses the Python
-    functions."""
+    None when the input cannot take the fast path (missing profiles); the caller then uses the Python functions.
+    The profile column is read in place through its Arrow buffers and the unique profile strings come back the same
+    way; the native pass runs on `threads` host threads (host_threads() by default)."""
+    import pyarrow as pa
     from .breakfast import _INVALID, _token_classifier
 
-    feats = meta["feature"].tolist()
-    n_seq = len(feats)
-    if n_seq == 0 or any(isinstance(f, float) for f in feats):
-        return None
-    joined = "\x00".join(feats)
-    if joined.count("\x00") != n_seq - 1:
-        return None
-    lib = _load()
-    buf = joined.encode("utf-8")
+    n_seq = len(meta)
     sep_b = feature_sep.encode("utf-8")
-    if not sep_b:
+    if n_seq == 0 or not sep_b:
         return None
-    state = lib.bfh_tokenise(buf, len(buf), b"\x00", sep_b, len(sep_b), n_seq)
+    view = _arrow_strings(meta["feature"])
+    if view is None:
+        return None
+    arr, data_ptr, off_ptr, width = view
+    lib = _load()
+    state = lib.bfh_tokenise_arrow(data_ptr, off_ptr, width, n_seq, sep_b, len(sep_b), int(threads or host_threads()))
     if not state:
         return None
     try:
@@ -109,26 +136,33 @@ def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, tri
         b_ptr = np.empty(n_unique + 1, dtype=np.int64)
         b_idx = np.empty(lib.bfh_binary_nnz(state), dtype=np.int32)
         s_off = np.empty(n_unique + 1, dtype=np.int64)
-        s_bytes = C.create_string_buffer(max(1, lib.bfh_string_bytes(state)))
+        s_bytes = np.empty(max(1, lib.bfh_string_bytes(state)), dtype=np.uint8)
         lib.bfh_get_results(state, codes.ctypes.data, first_seq.ctypes.data, invalid.ctypes.data, u_ptr.ctypes.data,
-                            u_idx.ctypes.data, b_ptr.ctypes.data, b_idx.ctypes.data, s_off.ctypes.data, s_bytes)
+                            u_idx.ctypes.data, b_ptr.ctypes.data, b_idx.ctypes.data, s_off.ctypes.data, s_bytes.ctypes.data)
         n_vocab, n_cols = lib.bfh_n_vocab(state), lib.bfh_n_cols(state)
     finally:
         lib.bfh_free(state)
+    del arr
 
     if filter_active and feature_type != "raw":
         assert _INVALID == 2
         for t in invalid.tolist():
             print(f"Skipping invalid feature: '{tokens[t]}'")
     print(f"Number of duplicates: {n_seq - n_unique}")
-    order = np.argsort(codes, kind="stable")
-    bounds = np.concatenate(([0], np.cumsum(np.bincount(codes, minlength=n_unique))))
-    ids = meta["id"].to_numpy(dtype=object)[order]
-    grouped = np.empty(n_unique, dtype=object)
-    for g in range(n_unique):
-        grouped[g] = tuple(ids[bounds[g]:bounds[g + 1]])
-    sraw = s_bytes.raw
-    strings = [sraw[s_off[u]:s_off[u + 1]].decode("utf-8") for u in range(n_unique)]
+    # ids of every unique profile as a tuple, in first-appearance order of the profiles
+    ids = meta["id"].to_numpy(dtype=object)
+    if n_unique == n_seq:
+        grouped = list(zip(ids.tolist()))
+    else:
+        order = np.argsort(codes, kind="stable")
+        counts = np.bincount(codes, minlength=n_unique)
+        bounds = np.concatenate(([0], np.cumsum(counts)))
+        ids_sorted = ids[order]
+        grouped = list(zip(ids_sorted[bounds[:-1]].tolist()))          # right for the single-sequence profiles
+        for g in np.flatnonzero(counts > 1).tolist():
+            grouped[g] = tuple(ids_sorted[bounds[g]:bounds[g + 1]])
+    # the unique profile strings as an Arrow string column built on the native buffers (no per-string decode)
+    strings = pa.LargeStringArray.from_buffers(n_unique, pa.py_buffer(s_off), pa.py_buffer(s_bytes))
     nodups = pd.DataFrame({"id": pd.Series(grouped, dtype=object),
                            "feature": pd.Series(strings, dtype=meta["feature"].dtype)})
     print(f"Number of unique sequences: {n_unique}")
