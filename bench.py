@@ -315,7 +315,7 @@ def main():
     # the compact host form of the same matrix (bf_csr16_encode: 32-bit offsets, 16-bit columns + a split per row), in
     # pinned memory: what the N = 1 e2e leg ships every step when the matrix is representable
     csr16 = None
-    if world == 1 and n_cols <= 131072 and int(np.diff(indptr).max(initial=0)) <= 65535:
+    if n_cols <= 131072 and int(np.diff(indptr).max(initial=0)) <= 65535:
         sizes = ((n + 1) * 4, n * 2 if n_cols > 65536 else 0, int(indices.size) * 2)
         ptrs = []
         for nb in sizes:
@@ -438,40 +438,27 @@ def main():
     #   N = 1: bf_upload_csr_async double-buffers, so the H2D of step k+1 overlaps the pass of step k.
     #   N > 1: every rank copies 1/N of the column array, the slices are all-gathered over NVLink (NCCL) and
     #          adopted in place (bf_adopt_csr_device); then the pass, the label all-gather + merge, and D2H.
-    if world == 1:
-        if csr16 is not None:
-            (q_ip, q_split, q_lo), sizes = csr16
-            h2d_bytes = int(sum(sizes))
+    if csr16 is not None:
+        # compact host form; with N ranks every rank copies 1/N of the 16-bit column array over its own host link and the
+        # shares are all-gathered over NVLink inside the library (copy stream, its own communicator), then decoded
+        (q_ip, q_split, q_lo), sizes = csr16
+        h2d_bytes = int(sizes[0] + sizes[1] + -(-sizes[2] // world))
 
-            def upload():
-                ctx.upload_csr16_async_ptr(q_ip.value, q_split.value if sizes[1] else None, q_lo.value, n, n_cols)
-        else:
-            h2d_bytes = int(indptr.nbytes + indices.nbytes)
-
-            def upload():
-                ctx.upload_csr_async_ptr(p_indptr.value, p_indices.value, n, n_cols)
-
-        def e2e_loop(k_steps):
-            upload()
-            for k in range(k_steps):
-                runner.step(MAX_DIST)                         # waits for the upload of this step
-                if k + 1 < k_steps:
-                    upload()                                  # overlaps the pass
-                _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+        def upload():
+            ctx.upload_csr16_async_ptr(q_ip.value, q_split.value if sizes[1] else None, q_lo.value, n, n_cols)
     else:
-        from breakfast_b200.dist import ShardedCsrUploader
-        uploader = ShardedCsrUploader(ctx, indptr, indices, n_cols, rank, world)
-        h2d_bytes = int(uploader.h2d_bytes)
+        h2d_bytes = int(indptr.nbytes + indices.nbytes)
 
-        def e2e_loop(k_steps):
-            uploader.prefetch()
-            for k in range(k_steps):
-                uploader.activate()                           # compute stream waits for this step's CSR
-                if k + 1 < k_steps:
-                    uploader.prefetch()                       # next step's copy + all-gather on the side stream
-                runner.step(MAX_DIST)
-                uploader.release()
-                _native._ck(lib.bf_download_labels(ctx._h, p_labels))
+        def upload():
+            ctx.upload_csr_async_ptr(p_indptr.value, p_indices.value, n, n_cols)
+
+    def e2e_loop(k_steps):
+        upload()
+        for k in range(k_steps):
+            runner.step(MAX_DIST)                         # waits for the upload of this step
+            if k + 1 < k_steps:
+                upload()                                  # overlaps the pass
+            _native._ck(lib.bf_download_labels(ctx._h, p_labels))
 
     e2e_loop(3)
     barrier()
@@ -532,9 +519,9 @@ def main():
             "e2e": {"value": st.pairs_band / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(labels_host.nbytes),
                     "input_path": ("compact host form (bf_upload_csr16_async: 32-bit offsets + 16-bit columns + per-row split, decoded on the "
-                                   "device), double-buffered: copy and decode of step k+1 overlap pass k" if csr16 is not None else
-                                   "double-buffered async H2D (copy of step k+1 overlaps pass k)") if world == 1 else
-                                  "per-rank 1/N H2D + NCCL all-gather of the CSR over NVLink, double-buffered on a side stream",
+                                   "device), double-buffered: copy and decode of step k+1 overlap pass k"
+                                   + ("; every rank copies 1/N of the columns, NCCL all-gather over NVLink in the library" if world > 1 else "")
+                                   if csr16 is not None else "double-buffered async H2D of the plain CSR (copy of step k+1 overlaps pass k)"),
                     "labels_sane": ok, "labels_sha256": labels_sha},
             "gpu_launches": int(launches),
             "roofline": dict({"kernel": kernel_name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit_r,

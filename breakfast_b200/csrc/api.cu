@@ -27,6 +27,7 @@ struct Api {
     int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
     int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
     int (*CommDestroy)(comm_t) = nullptr;
+    int (*CommSplit)(comm_t, int, int, comm_t*, void*) = nullptr;   // optional (NCCL >= 2.18)
     int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
@@ -52,6 +53,7 @@ inline Api& api() {
     a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
     a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
     a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.CommSplit = (decltype(a.CommSplit))sym("ncclCommSplit");
     a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
     a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
@@ -162,6 +164,7 @@ struct bf_ctx {
 
     // communicator of a multi-GPU job (NCCL); with it bf_run does its own exchange steps
     bfnccl::comm_t comm = nullptr;
+    bfnccl::comm_t comm_copy = nullptr;   // a duplicate of `comm` for collectives on the copy stream (sharded uploads)
     int comm_rank = 0, comm_world = 1;
     int64_t merge_capacity = 0;   // entries per rank of the compact label exchange, 0 = automatic
     int64_t merge_auto = 0;       // automatic capacity learnt from earlier passes (what the fullest list needed, + 25 %)
@@ -291,9 +294,12 @@ inline bool staged_pack(const bf_ctx* c) {
 // rows the staging arrays must hold: with a communicator every rank owns an equal, block-aligned share (the last ones
 // possibly past the end), so that the shares can be all-gathered in place
 inline bool dist_run(const bf_ctx* c) { return c->comm != nullptr && c->world > 1; }
+// The sketch + key pass is sharded over the ranks only from 8 ranks on: the all-gather of the shares costs about 0.08 ms
+// on NVLink whatever the rank count (measured, profiles/r02_scale_*), the pass itself 0.115 ms / world
+inline bool shard_pack(const bf_ctx* c) { return dist_run(c) && c->world >= 8; }
 inline int64_t staged_rows(const bf_ctx* c) {
     const int64_t blocks = ceil_div(c->n_rows, TILE);
-    return dist_run(c) ? ceil_div(blocks, c->world) * c->world * TILE : blocks * TILE;
+    return shard_pack(c) ? ceil_div(blocks, c->world) * c->world * TILE : blocks * TILE;
 }
 
 int pack_stage_all_rows(bf_ctx* c) {
@@ -307,7 +313,7 @@ int pack_stage_all_rows(bf_ctx* c) {
     CK(cudaMemsetAsync(or_key, 0, 2 * sizeof(sortkey_t), c->stream));
     const int64_t blocks = ceil_div(n, TILE);
     int64_t block0 = 0, my_blocks = blocks, share = blocks;
-    if (dist_run(c)) {   // this rank streams only its share of the rows; the shares are exchanged below
+    if (shard_pack(c)) {   // this rank streams only its share of the rows; the shares are exchanged below
         share = ceil_div(blocks, c->world);
         block0 = share * c->rank;
         my_blocks = std::max<int64_t>(0, std::min(share, blocks - block0));
@@ -321,7 +327,7 @@ int pack_stage_all_rows(bf_ctx* c) {
                                                                              c->keysB[0].as<sortkey_t>(), c->valsB[0].as<int32_t>(), or_key, block0);
         CKLC(c);
     }
-    if (dist_run(c)) {
+    if (shard_pack(c)) {
         // exchange step 1: all-gather of the sketch and key shares (16 + 8 bytes per row at 128 bits) over NVLink,
         // in place; then row numbers and the OR word over all keys
         bfnccl::Api& nc = bfnccl::api();
@@ -647,6 +653,11 @@ void bf_ctx_destroy(bf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_copy) {
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        bfnccl::api().CommDestroy(c->comm_copy);
+        c->comm_copy = nullptr;
+    }
     if (c->comm) {
         bfnccl::api().CommDestroy(c->comm);
         c->comm = nullptr;
@@ -860,7 +871,23 @@ int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* s
     CK(cudaEventRecord(c->ev_upload_start, c->copy_stream));
     CK(cudaMemcpyAsync(c->c16_indptr[slot].p, indptr32, (size_t)(n_rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
     if (split) CK(cudaMemcpyAsync(c->c16_split[slot].p, split, (size_t)n_rows * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
-    if (nnz > 0) CK(cudaMemcpyAsync(c->c16_lo[slot].p, lo, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (nnz > 0) {
+        if (c->comm_copy && c->comm_world > 1) {
+            // multi-GPU job (every rank makes this call with the same matrix): this rank copies only its share of the
+            // column array over its own host link, the shares are all-gathered over NVLink on the copy stream
+            const int W = c->comm_world;
+            const size_t share = (size_t)((ceil_div(nnz, W) + 7) & ~(int64_t)7);   // entries per rank, 16-byte aligned
+            TRY(c->c16_lo[slot].ensure(share * W * sizeof(uint16_t)));
+            const size_t lo0 = std::min<size_t>((size_t)nnz, share * c->comm_rank), lo1 = std::min<size_t>((size_t)nnz, lo0 + share);
+            char* base = c->c16_lo[slot].as<char>();
+            if (lo1 > lo0)
+                CK(cudaMemcpyAsync(base + lo0 * sizeof(uint16_t), lo + lo0, (lo1 - lo0) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+            NCK(bfnccl::api().AllGather(base + share * c->comm_rank * sizeof(uint16_t), base, share * sizeof(uint16_t), bfnccl::kUint8,
+                                        c->comm_copy, c->copy_stream));
+        } else {
+            CK(cudaMemcpyAsync(c->c16_lo[slot].p, lo, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+        }
+    }
     // decode on the copy stream as well: it overlaps the pass that is still running on the other slot
     k_csr16_decode<<<c->num_sms * 8, 256, 0, c->copy_stream>>>(c->c16_indptr[slot].as<uint32_t>(), split ? c->c16_split[slot].as<uint16_t>() : nullptr,
                                                                c->c16_lo[slot].as<uint16_t>(), n_rows, c->indptr[slot].as<int64_t>(),
@@ -1136,6 +1163,7 @@ int bf_ctx_comm_init_rank(bf_ctx* c, const void* id, int32_t rank, int32_t world
     NCK(nc.CommInitRank(&c->comm, world, uid, rank));
     c->comm_rank = rank;
     c->comm_world = world;
+    if (nc.CommSplit && world > 1) NCK(nc.CommSplit(c->comm, 0, rank, &c->comm_copy, nullptr));   // collective: every rank does it
     return BF_OK;
 }
 
@@ -1158,6 +1186,11 @@ int bf_comm_init_all(bf_ctx** ctxs, int32_t n) {
         ctxs[i]->comm_rank = i;
         ctxs[i]->comm_world = n;
     }
+    if (nc.CommSplit && n > 1) {   // duplicates for the copy streams
+        NCK(nc.GroupStart());
+        for (int i = 0; i < n; ++i) NCK(nc.CommSplit(ctxs[i]->comm, 0, i, &ctxs[i]->comm_copy, nullptr));
+        NCK(nc.GroupEnd());
+    }
     return BF_OK;
 }
 
@@ -1166,6 +1199,11 @@ int bf_ctx_comm_destroy(bf_ctx* c) {
     if (!c->comm) return BF_OK;
     TRY(set_device(c));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->comm_copy) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        NCK(bfnccl::api().CommDestroy(c->comm_copy));
+        c->comm_copy = nullptr;
+    }
     NCK(bfnccl::api().CommDestroy(c->comm));
     c->comm = nullptr;
     c->comm_rank = 0;
