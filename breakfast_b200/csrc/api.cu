@@ -189,7 +189,16 @@ struct bf_ctx {
     // CSR on the device: two owned slots (async uploads fill the idle one while a pass runs on the
     // other) or caller-owned memory (bf_adopt_csr_device); d_indptr/d_indices is what kernels read
     DevBuf indptr[2], indices[2], query_rows, is_query;
-    DevBuf c16_indptr[2], c16_split[2], c16_lo[2];   // staging of the compact host form, one set per slot
+    // the compact resident form ("CSR16": uint32 offsets, uint16 low column halves, uint16 split per row), one set per
+    // slot: uploaded as such (bf_upload_csr16_async) or derived on the device once per upload (bf_upload_csr).  The staged
+    // sketch pass (the one kernel that streams the whole matrix) reads it instead of the plain CSR - half the bytes.  The
+    // plain form is always there as well: the verification and the other engines walk single rows of it.
+    DevBuf c16_indptr[2], c16_split[2], c16_lo[2], c16_bad;
+    bool c16_valid[2] = {false, false}, c16_has_split[2] = {false, false};
+    int resident16 = 1;    // option "resident_csr16": 0 = the sketch pass streams the plain CSR
+    int pack16_variant = 1;   // one lane per row, ATOMS (fastest of the four, profiles/)
+    int active_slot = -1;  // slot the current matrix lives in, -1 = caller-owned memory (bf_adopt_csr_device) or none
+    bool use16 = false;    // this pass's sketch kernel reads the compact form
     DevBuf hj_hash, hj_t1, hj_t2, hj_t2_rows;        // hash-join engine: row hashes, row table, one-deletion table
     const int64_t* d_indptr = nullptr;
     const int32_t* d_indices = nullptr;
@@ -289,6 +298,21 @@ inline bool staged_pack(const bf_ctx* c) {
     return c->engine == BF_ENGINE_SKETCH && (c->sketch_bits == 128 || c->sketch_bits == 256);
 }
 
+// plain CSR of `slot` -> compact resident form of the same slot (k_csr16_encode); c16_bad tells afterwards whether the
+// matrix was representable
+int encode_c16(bf_ctx* c, int slot, int64_t n_rows, int64_t nnz, cudaStream_t stream) {
+    TRY(c->c16_indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(uint32_t)));
+    TRY(c->c16_split[slot].ensure((size_t)n_rows * sizeof(uint16_t)));
+    TRY(c->c16_lo[slot].ensure((size_t)(nnz + 8) * sizeof(uint16_t)));   // + 16 bytes: bulk copies end on a 16-byte boundary
+    TRY(c->c16_bad.ensure(sizeof(int)));
+    CK(cudaMemsetAsync(c->c16_bad.p, 0, sizeof(int), stream));
+    k_csr16_encode<<<c->num_sms * 8, 256, 0, stream>>>(c->indptr[slot].as<int64_t>(), c->indices[slot].as<int32_t>(), n_rows,
+                                                       c->c16_indptr[slot].as<uint32_t>(), c->c16_split[slot].as<uint16_t>(),
+                                                       c->c16_lo[slot].as<uint16_t>(), c->c16_bad.as<int>());
+    CKLC(c);
+    return BF_OK;
+}
+
 // step 1 of the staged pack: sketches + sort keys of ALL rows of the matrix in storage order (the B side is the
 // whole matrix; a query subset reads its rows' sketches and keys from the same staging arrays)
 // rows the staging arrays must hold: with a communicator every rank owns an equal, block-aligned share (the last ones
@@ -318,7 +342,28 @@ int pack_stage_all_rows(bf_ctx* c) {
         block0 = share * c->rank;
         my_blocks = std::max<int64_t>(0, std::min(share, blocks - block0));
     }
-    if (my_blocks > 0) {
+    if (my_blocks > 0 && c->use16) {
+        const uint32_t* ip = c->c16_indptr[c->cur].as<uint32_t>();
+        const uint16_t* sp = c->c16_has_split[c->cur] ? c->c16_split[c->cur].as<uint16_t>() : nullptr;
+        const uint16_t* lo = c->c16_lo[c->cur].as<uint16_t>();
+        // variants (option pack16_variant = lanes per row + 4 * [plain read-modify-write instead of ATOMS]): measured
+        // in profiles/, the default is PACK16_DEFAULT
+        const int v = c->pack16_variant;
+        auto pack16 = k_pack_sketch_rows16<4, 2, true>;
+        int lanes = 2;
+#define BF_PACK16(W)                                                                                     \
+        switch (v) {                                                                                     \
+            case 1: pack16 = k_pack_sketch_rows16<W, 1, true>; lanes = 1; break;                         \
+            case 5: pack16 = k_pack_sketch_rows16<W, 1, false>; lanes = 1; break;                        \
+            case 6: pack16 = k_pack_sketch_rows16<W, 2, false>; lanes = 2; break;                        \
+            default: pack16 = k_pack_sketch_rows16<W, 2, true>; lanes = 2; break;                        \
+        }
+        if (words == 4) { BF_PACK16(4) } else { BF_PACK16(8) }
+#undef BF_PACK16
+        pack16<<<(unsigned)my_blocks, TILE * lanes, 0, c->stream>>>(ip, sp, lo, n, c->sk_rows.as<uint32_t>(), c->keysB[0].as<sortkey_t>(),
+                                                                     c->valsB[0].as<int32_t>(), or_key, block0);
+        CKLC(c);
+    } else if (my_blocks > 0) {
         if (words == 4)
             k_pack_sketch_rows<4><<<(unsigned)my_blocks, 256, 0, c->stream>>>(c->d_indptr, c->d_indices, n, log2m, c->sk_rows.as<uint32_t>(),
                                                                              c->keysB[0].as<sortkey_t>(), c->valsB[0].as<int32_t>(), or_key, block0);
@@ -663,7 +708,7 @@ void bf_ctx_destroy(bf_ctx* c) {
         c->comm = nullptr;
     }
     DevBuf* bufs[] = {&c->indptr[0], &c->indptr[1], &c->indices[0], &c->indices[1], &c->query_rows, &c->is_query,
-                      &c->hj_hash, &c->hj_t1, &c->hj_t2, &c->hj_t2_rows, &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->keysB[0], &c->keysB[1], &c->keysB[2],
+                      &c->hj_hash, &c->hj_t1, &c->hj_t2, &c->hj_t2_rows, &c->c16_indptr[0], &c->c16_indptr[1], &c->c16_split[0], &c->c16_split[1], &c->c16_lo[0], &c->c16_lo[1], &c->c16_bad, &c->keysB[0], &c->keysB[1], &c->keysB[2],
                       &c->valsB[0], &c->valsB[1], &c->valsB[2], &c->keysA[0], &c->keysA[1], &c->keysA[2], &c->valsA[0], &c->valsA[1], &c->valsA[2], &c->sched_table,
                       &c->sort_counts, &c->sort_max, &c->sk_rows, &c->xchg, &c->band_cache, &c->bitsA, &c->bitsB, &c->foldsA[0], &c->foldsA[1], &c->foldsB[0], &c->foldsB[1], &c->fold8A[0], &c->fold8A[1], &c->fold8B[0], &c->fold8B[1], &c->jlo, &c->jend, &c->queue, &c->segcnt, &c->wprefix, &c->nwork, &c->items, &c->cand,
                       &c->edges, &c->parent, &c->labels, &c->counters, &c->scratch, &c->scratch2};
@@ -709,6 +754,11 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "units_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "units_capacity must be >= 0");
         c->units_capacity = value;
+    } else if (k == "pack16_variant") {
+        if (value != 1 && value != 2 && value != 5 && value != 6) return fail(BF_ERR_INVALID, "pack16_variant must be 1, 2, 5 or 6");
+        c->pack16_variant = (int)value;
+    } else if (k == "resident_csr16") {
+        c->resident16 = value ? 1 : 0;   // 0: the sketch pass streams the plain CSR
     } else if (k == "blocks_per_sm") {
         if (value < 0 || value > 8) return fail(BF_ERR_INVALID, "blocks_per_sm must be in [0, 8]");
         c->blocks_per_sm = (int)value;
@@ -761,6 +811,13 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
     }
     c->d_indptr = dip.as<int64_t>();
     c->d_indices = dix.as<int32_t>();
+    c->active_slot = c->cur;
+    c->c16_valid[c->cur] = false;
+    bool encoded = false;
+    if (c->resident16 && n_rows > 0 && nnz > 0 && n_cols <= 131072 && nnz < ((int64_t)1 << 32)) {
+        TRY(encode_c16(c, c->cur, n_rows, nnz, c->stream));   // compact resident form, checked on the device
+        encoded = true;
+    }
     c->has_query = query_rows != nullptr;
     c->n_query = c->has_query ? n_query : n_rows;
     if (c->has_query) {
@@ -777,6 +834,12 @@ int bf_upload_csr(bf_ctx* c, const int64_t* indptr, const int32_t* indices, int6
     // the caller's buffers may be pageable and are not retained: wait for the copies
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&c->ms_h2d, c->ev_aux[0], c->ev_aux[1]));
+    if (encoded) {
+        int bad = 1;
+        CK(cudaMemcpy(&bad, c->c16_bad.p, sizeof bad, cudaMemcpyDeviceToHost));
+        c->c16_valid[c->cur] = bad == 0;   // not representable after all: the plain form stays in charge
+        c->c16_has_split[c->cur] = true;
+    }
     c->n_rows = n_rows;
     c->n_cols = n_cols;
     c->nnz = nnz;
@@ -796,10 +859,11 @@ int bf_upload_csr_async(bf_ctx* c, const int64_t* indptr, const int32_t* indices
     if (nnz > 0 && !indices) return fail(BF_ERR_INVALID, "indices is null");
     TRY(set_device(c));
     if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is already pending; call bf_run first");
-    const int slot = (c->d_indptr == c->indptr[c->cur].as<int64_t>() && c->d_indptr) ? c->cur ^ 1 : c->cur;
+    const int slot = c->active_slot >= 0 ? c->active_slot ^ 1 : c->cur;
     TRY(c->indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
     TRY(c->indices[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     if (c->slot_used[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_free[slot], 0));
+    c->c16_valid[slot] = false;   // (the plain form only: nothing checks the columns on this path)
     CK(cudaEventRecord(c->ev_upload_start, c->copy_stream));
     CK(cudaMemcpyAsync(c->indptr[slot].p, indptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
     if (nnz > 0) CK(cudaMemcpyAsync(c->indices[slot].p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
@@ -861,11 +925,11 @@ int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* s
     if (n_cols > 65536 && !split) return fail(BF_ERR_INVALID, "split is needed when n_cols > 65536");
     TRY(set_device(c));
     if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is already pending; call bf_run first");
-    const int slot = (c->d_indptr == c->indptr[c->cur].as<int64_t>() && c->d_indptr) ? c->cur ^ 1 : c->cur;
+    const int slot = c->active_slot >= 0 ? c->active_slot ^ 1 : c->cur;
     TRY(c->indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(int64_t)));
     TRY(c->indices[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     TRY(c->c16_indptr[slot].ensure((size_t)(n_rows + 1) * sizeof(uint32_t)));
-    TRY(c->c16_lo[slot].ensure((size_t)std::max<int64_t>(nnz, 1) * sizeof(uint16_t)));
+    TRY(c->c16_lo[slot].ensure((size_t)(nnz + 8) * sizeof(uint16_t)));   // + 16 bytes: bulk copies end on a 16-byte boundary
     if (split) TRY(c->c16_split[slot].ensure((size_t)n_rows * sizeof(uint16_t)));
     if (c->slot_used[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_free[slot], 0));
     CK(cudaEventRecord(c->ev_upload_start, c->copy_stream));
@@ -877,7 +941,7 @@ int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* s
             // column array over its own host link, the shares are all-gathered over NVLink on the copy stream
             const int W = c->comm_world;
             const size_t share = (size_t)((ceil_div(nnz, W) + 7) & ~(int64_t)7);   // entries per rank, 16-byte aligned
-            TRY(c->c16_lo[slot].ensure(share * W * sizeof(uint16_t)));
+            TRY(c->c16_lo[slot].ensure((share * W + 8) * sizeof(uint16_t)));
             const size_t lo0 = std::min<size_t>((size_t)nnz, share * c->comm_rank), lo1 = std::min<size_t>((size_t)nnz, lo0 + share);
             char* base = c->c16_lo[slot].as<char>();
             if (lo1 > lo0)
@@ -888,11 +952,14 @@ int bf_upload_csr16_async(bf_ctx* c, const uint32_t* indptr32, const uint16_t* s
             CK(cudaMemcpyAsync(c->c16_lo[slot].p, lo, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
         }
     }
-    // decode on the copy stream as well: it overlaps the pass that is still running on the other slot
+    // decode on the copy stream as well (it overlaps the pass that is still running on the other slot): the
+    // verification and the other engines walk rows of the plain CSR; the compact form stays resident for the sketch pass
     k_csr16_decode<<<c->num_sms * 8, 256, 0, c->copy_stream>>>(c->c16_indptr[slot].as<uint32_t>(), split ? c->c16_split[slot].as<uint16_t>() : nullptr,
                                                                c->c16_lo[slot].as<uint16_t>(), n_rows, c->indptr[slot].as<int64_t>(),
                                                                c->indices[slot].as<int32_t>());
     CKLC(c);
+    c->c16_valid[slot] = true;
+    c->c16_has_split[slot] = split != nullptr;
     CK(cudaEventRecord(c->ev_upload_done, c->copy_stream));
     c->pending = slot;
     c->pend_rows = n_rows;
@@ -911,6 +978,7 @@ int bf_adopt_csr_device(bf_ctx* c, const void* indptr_device, const void* indice
     if (c->pending >= 0) return fail(BF_ERR_STATE, "an async upload is pending");
     c->d_indptr = static_cast<const int64_t*>(indptr_device);
     c->d_indices = static_cast<const int32_t*>(indices_device);
+    c->active_slot = -1;
     c->n_rows = c->n_query = n_rows;
     c->n_cols = n_cols;
     c->nnz = nnz;
@@ -937,6 +1005,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_upload_done, 0));
         c->cur = c->pending;
         c->pending = -1;
+        c->active_slot = c->cur;
         c->d_indptr = c->indptr[c->cur].as<int64_t>();
         c->d_indices = c->indices[c->cur].as<int32_t>();
         c->n_rows = c->n_query = c->pend_rows;
@@ -951,6 +1020,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     c->ran = false;
     c->ms_merge = 0;
     const int64_t nB = c->n_rows, nA = c->n_query;
+    // the staged sketch pass streams the compact form of the matrix where the slot holds it
+    c->use16 = c->resident16 && staged_pack(c) && c->active_slot >= 0 && c->c16_valid[c->cur];
 
     const bool hashjoin = c->engine == BF_ENGINE_HASHJOIN;
     if (hashjoin) {
@@ -1109,17 +1180,23 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(ring[2], c->stream));
     if (active) {
         // ---- K3b: verify + hook
-        auto verify = k_verify_unite<0>;   // window = max_dist: a wider compile-time window would still be exact
-        if (max_dist == 1) verify = k_verify_unite<1>;
-        else if (max_dist == 2) verify = k_verify_unite<2>;
-        else if (max_dist == 3) verify = k_verify_unite<3>;
-        int vbps = 0;   // grid-stride kernel: launch exactly the blocks that are resident at once
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, verify, 256, 0));
-        verify<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
-            c->cand.as<uint2>(), c->cand_cap_used, hashjoin ? nullptr : valsA[0].as<int32_t>(), hashjoin ? nullptr : c->valsB[0].as<int32_t>(),
-            c->d_indptr, c->d_indices, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0,
-            (c->has_query && !hashjoin) ? c->is_query.as<unsigned char>() : nullptr, c->parent.as<int>(),
-            c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
+        RowStore rows{};
+        const int32_t* pA = hashjoin ? nullptr : valsA[0].as<int32_t>();
+        const int32_t* pB = hashjoin ? nullptr : c->valsB[0].as<int32_t>();
+        const unsigned char* isq = (c->has_query && !hashjoin) ? c->is_query.as<unsigned char>() : nullptr;
+        {
+            auto verify = k_verify_unite<0>;   // window = max_dist: a wider compile-time window would still be exact
+            if (max_dist == 1) verify = k_verify_unite<1>;
+            else if (max_dist == 2) verify = k_verify_unite<2>;
+            else if (max_dist == 3) verify = k_verify_unite<3>;
+            rows.indptr = c->d_indptr;
+            rows.indices = c->d_indices;
+            int vbps = 0;   // grid-stride kernel: launch exactly the blocks that are resident at once
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, verify, 256, 0));
+            verify<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
+                c->cand.as<uint2>(), c->cand_cap_used, pA, pB, rows, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0, isq,
+                c->parent.as<int>(), c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
+        }
         CKLC(c);
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
@@ -1129,7 +1206,7 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     TRY(finish_labels(c));
     CK(cudaEventRecord(c->ev[6], c->stream));
     CK(cudaEventRecord(ring[3], c->stream));
-    if (c->d_indptr == c->indptr[c->cur].as<int64_t>()) {
+    if (c->active_slot >= 0) {
         CK(cudaEventRecord(c->ev_slot_free[c->cur], c->stream));  // the idle slot may be refilled after this
         c->slot_used[c->cur] = true;
     }

@@ -482,6 +482,43 @@ __host__ __device__ inline int fold_pos_b(int row) { return (row & 31) * 4 + (ro
 // level-2 unit order of the tensor-core level 1: lane l of a warp holds rows (l/4) + 8 s, s < 16, of the tile
 __host__ __device__ inline int imma_unit_pos(int row) { return (row & 7) * 16 + (row >> 3); }
 
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-async-copy (TMA, SASS UBLKCP) wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // 16 bits -> 16 int8 values (+1 for a clear bit, -1 for a set bit)
 __device__ __forceinline__ uint4 expand_pm1(uint32_t bits16) {
     uint32_t w[4];
@@ -653,6 +690,135 @@ __global__ void __launch_bounds__(256) k_pack_sketch_rows(const int64_t* __restr
     or_reduce_key(key, or_key);
 }
 
+// The same step on the COMPACT RESIDENT FORM of the matrix ("CSR16", see k_csr16_encode / include/breakfast_b200.h:
+// 32-bit row offsets, the low 16 bits of every column, per row the number of columns below 65536) - half the bytes of
+// the plain CSR.  A block takes 128 consecutive rows.  Their columns are one contiguous stretch of `lo`: thread 0
+// fetches it with 1-D bulk-async copies (TMA, completion on an mbarrier) in chunks of PACK16_CHUNK entries - one chunk
+// for rows of up to 128 columns on average.  LPR lanes then walk every row out of shared memory (lane j takes columns
+// j, j + LPR, ...).  A lane toggles the bits of its columns in a sketch of its own in shared memory (word w of thread t
+// at priv[w][t]: bank = t mod 32, conflict-free, no other thread touches it), so the word select costs one address
+// computation instead of one compare + XOR per word; the two quadrant counters ride in registers (2|H1| + |H2| and
+// |H1|).  Row lengths differ a lot (40 ... 145 columns in SARS-CoV-2 profiles), and a warp takes as long as its longest
+// row: the rows of a block are therefore dealt to the threads in order of length (a 64-bin counting sort in shared
+// memory), which keeps the lanes of a warp within a few columns of each other.
+// Reads 2 nnz + 6 N bytes, writes N (m/8 + 12) bytes; the sketch does not depend on which thread folded which row.
+constexpr int PACK16_CHUNK = 16384;   // entries (32 KB of shared memory)
+constexpr int PACK16_LANES = 2;       // lanes per row
+template <int WORDS, int LPR, bool ATOM>
+__global__ void __launch_bounds__(TILE * LPR) k_pack_sketch_rows16(const uint32_t* __restrict__ indptr32,
+                                                                   const uint16_t* __restrict__ split,
+                                                                   const uint16_t* __restrict__ lo, int64_t n,
+                                                                   uint32_t* __restrict__ sk_rows, sortkey_t* __restrict__ keys,
+                                                                   int32_t* __restrict__ vals, sortkey_t* __restrict__ or_key,
+                                                                   int64_t block0) {
+    static_assert(WORDS == 4 || WORDS == 8, "128- or 256-bit sketches");
+    static_assert(LPR == 1 || LPR == 2, "one or two lanes per row");
+    constexpr int LOG2M = WORDS == 4 ? 7 : 8;
+    constexpr int NT = TILE * LPR;
+    __shared__ __align__(16) uint16_t cols[PACK16_CHUNK + 8];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t priv[WORDS][NT];
+    __shared__ uint32_t row_b[TILE + 1];
+    __shared__ uint16_t row_s[TILE];
+    __shared__ int bins[64];
+    __shared__ unsigned char order[TILE];
+    const int64_t row0 = (block0 + (int64_t)blockIdx.x) * TILE;
+    const int tid = threadIdx.x;
+    if (tid < 64) bins[tid] = 0;
+#pragma unroll
+    for (int t = 0; t < WORDS; ++t) priv[t][tid] = 0u;
+    for (int i = tid; i <= TILE; i += NT) {
+        row_b[i] = __ldg(&indptr32[min(row0 + i, n)]);
+        if (i < TILE) row_s[i] = (split && row0 + i < n) ? __ldg(&split[row0 + i]) : (uint16_t)0xffffu;
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // rows in order of length: counting sort on length / 4 (clamped), ties in any order
+    int my_bin = 0;
+    if (tid < TILE) {
+        my_bin = (int)min((row_b[tid + 1] - row_b[tid]) >> 2, 63u);
+        atomicAdd(&bins[my_bin], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the 64 bins by one warp
+        const int a = bins[2 * tid], b2 = bins[2 * tid + 1];
+        int incl = a + b2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        bins[2 * tid] = incl - a - b2;
+        bins[2 * tid + 1] = incl - b2;
+    }
+    __syncthreads();
+    if (tid < TILE) order[atomicAdd(&bins[my_bin], 1)] = (unsigned char)tid;
+    __syncthreads();
+    const int rt = order[tid / LPR], sub = tid % LPR;   // row of the block, lane of the row
+    const int64_t r = row0 + rt;
+    const uint32_t b = row_b[rt], e = row_b[rt + 1];
+    const uint32_t sp = row_s[rt] == 0xffffu && !split ? 0xffffffffu : (uint32_t)row_s[rt];
+    const uint32_t blk_b = row_b[0] & ~7u, blk_e = row_b[TILE];   // chunk starts stay 16-byte aligned
+    uint32_t quad = 0, in_h1 = 0, phase = 0;
+    const uint32_t hi_at = b + min(sp, e - b);   // first position of the row whose column is >= 65536
+    uint32_t* mine = &priv[0][tid];
+    for (uint32_t cb = blk_b; cb < blk_e; cb += PACK16_CHUNK) {
+        const uint32_t ce = min(cb + (uint32_t)PACK16_CHUNK, blk_e);
+        if (tid == 0) {
+            const uint32_t bytes = ((ce - cb) * 2u + 15u) & ~15u;   // the array is allocated with 16 bytes of slack
+            mbar_arrive_expect_tx(&bar, bytes);
+            bulk_g2s(cols, lo + cb, bytes, &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        const uint32_t kb = max(b, cb), ke = min(e, ce);
+        // lane `sub` takes the row's columns at positions = sub (mod LPR)
+        uint32_t k = kb + ((sub + LPR - ((kb - b) % LPR)) % LPR);
+        // fold_hash of column lo + 65536 [k >= hi_at]: h = h32 >> (32 - LOG2M); the multiplication distributes
+        auto fold = [&](uint32_t lo16, uint32_t kk) {
+            const uint32_t h32 = lo16 * 2654435761u + (kk >= hi_at ? 2654435761u << 16 : 0u);
+            const uint32_t bit = 1u << ((h32 >> (32 - LOG2M)) & 31u);
+            uint32_t* dst = mine + (h32 >> (37 - LOG2M)) * NT;   // word h >> 5 of this thread's sketch
+            if (ATOM) atomicXor(dst, bit);
+            else *dst ^= bit;
+            quad += h32 >> 30;    // 2 |row n H1| + |row n H2| ...
+            in_h1 += h32 >> 31;   // ... and |row n H1| (H1 / H2: hash bit 31 / 30 set)
+        };
+        for (; k + 3 * LPR < ke; k += 4 * LPR) {   // four columns per round: the loads first, all independent
+            uint32_t c4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c4[u] = cols[k + u * LPR - cb];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fold(c4[u], k + u * LPR);
+        }
+        for (; k < ke; k += LPR) fold(cols[k - cb], k);
+        __syncthreads();   // everyone is done with this chunk before the next copy lands
+    }
+    uint32_t w[WORDS];
+#pragma unroll
+    for (int t = 0; t < WORDS; ++t) w[t] = priv[t][tid];
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) {
+#pragma unroll
+        for (int t = 0; t < WORDS; ++t) w[t] ^= __shfl_xor_sync(0xffffffffu, w[t], o);
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        in_h1 += __shfl_xor_sync(0xffffffffu, in_h1, o);
+    }
+    sortkey_t key = 0;
+    if (sub == 0 && r < n) {
+        uint4* out = reinterpret_cast<uint4*>(sk_rows + (size_t)r * WORDS);
+#pragma unroll
+        for (int g = 0; g < WORDS / 4; ++g) out[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+        key = sort_key((int64_t)(e - b), in_h1, quad - 2u * in_h1);
+        keys[r] = key;
+        vals[r] = (int32_t)r;
+    }
+    or_reduce_key(key, or_key);
+}
+
 // step 2 of 2 (after the sort): thread p of block `tile` fetches the staged sketch of the row at sorted position
 // tile * 128 + p and writes all derived layouts of that slot (pack_store_row); pad slots are zero-filled.
 template <int WORDS>
@@ -694,42 +860,6 @@ __global__ void __launch_bounds__(256) k_pack_full(const int64_t* __restrict__ i
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// mbarrier / bulk-async-copy (TMA, SASS UBLKCP) wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 // K2c: explicit work list.  items[w] = (I, J) for every band tile pair, so that the pair kernel's
@@ -1521,11 +1651,114 @@ __global__ void k_uf_lists(int* __restrict__ parent, const int64_t* __restrict__
 // quantity sklearn's two-pointer merge accumulates (_pairwise_fast.pyx:83-105), on integers.  Hooks and the edge append are then done per
 // lane with one aggregated cursor update per batch.
 // ------------------------------------------------------------------------------------------
+// The plain CSR as the kernels that walk single rows see it
+struct RowStore {
+    const int64_t* indptr;
+    const int32_t* indices;
+};
+__device__ __forceinline__ int row_col(const RowStore& m, int64_t base, int k) { return __ldg(m.indices + base + k); }
+__device__ __forceinline__ void row_extent(const RowStore& m, int r, int64_t& base, int& len) {
+    base = __ldg(&m.indptr[r]);
+    len = (int)(__ldg(&m.indptr[r + 1]) - base);   // a row has fewer than 2^31 columns
+}
+
+// One chunk of 128 columns of the shorter row A and the longer row B of a candidate, lane t holding positions
+// base + t + 32 s (s < 4); lane t < NW also holds B[base - NW + t] and B[base + 128 + t] (the halo).
+template <int NW>
+__device__ __forceinline__ void verify_load_chunk(const RowStore& m, int lane, int base, int64_t ia, int la, int64_t ib, int lb,
+                                                  int (&av)[4], int (&bv)[4], int& halo_lo, int& halo_hi) {
+#pragma unroll
+    for (int sw = 0; sw < 4; ++sw) {
+        const int k = base + lane + 32 * sw;
+        av[sw] = k < la ? row_col(m, ia, k) : -2;   // column ids are >= 0: the fillers match nothing
+        bv[sw] = k < lb ? row_col(m, ib, k) : -1;
+    }
+    halo_lo = -1;
+    halo_hi = -1;
+    if (lane < NW) {
+        if (NW / 2 > 0 && base - NW + lane >= 0 && base - NW + lane < lb) halo_lo = row_col(m, ib, base - NW + lane);
+        if (base + 128 + lane < lb) halo_hi = row_col(m, ib, base + 128 + lane);
+    }
+}
+// How many of this lane's columns of A occur in B at the offsets -ND ... +NW: the neighbours of B come from lane
+// rotations.  A is the shorter row: with a = |A \ B|, b = |B \ A| (b - a = |B| - |A| >= 0, a + b <= d) a common column
+// sits at positions i in A and j in B with j - i in [-a, b], and a <= d / 2 - so the window below needs only half the
+// reach of the window above (none at all at max_dist 1).  A match outside the exact bounds is still a true common
+// column (the columns of a row are distinct), so the static window is sound.
+template <int NW>
+__device__ __forceinline__ int verify_match_chunk(int lane, const int (&av)[4], const int (&bv)[4], int halo_lo, int halo_hi) {
+    constexpr int ND = NW / 2;
+    constexpr int NDA = ND > 0 ? ND : 1;
+    int dn[4][NDA], up[4][NW];   // bv[sw] rotated by -o / +o lanes
+#pragma unroll
+    for (int sw = 0; sw < 4; ++sw) {
+#pragma unroll
+        for (int o = 1; o <= ND; ++o) dn[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane - o) & 31);
+#pragma unroll
+        for (int o = 1; o <= NW; ++o) up[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane + o) & 31);
+    }
+    // lane < o of the first sweep needs B[base + lane - o] = halo_lo of lane NW + lane - o;
+    // lane >= 32 - o of the last sweep needs B[base + 128 + lane + o - 32] = halo_hi of that lane
+    int hlo[NDA], hhi[NW];
+#pragma unroll
+    for (int o = 1; o <= ND; ++o) hlo[o - 1] = __shfl_sync(0xffffffffu, halo_lo, (NW + lane - o) & 31);
+#pragma unroll
+    for (int o = 1; o <= NW; ++o) hhi[o - 1] = __shfl_sync(0xffffffffu, halo_hi, (lane + o) & 31);
+    int hits = 0;
+#pragma unroll
+    for (int sw = 0; sw < 4; ++sw) {
+        bool hit = av[sw] == bv[sw];
+#pragma unroll
+        for (int o = 1; o <= ND; ++o) {
+            const int below = lane >= o ? dn[sw][o - 1] : (sw > 0 ? dn[sw - 1][o - 1] : hlo[o - 1]);        // B[k - o]
+            hit |= av[sw] == below;
+        }
+#pragma unroll
+        for (int o = 1; o <= NW; ++o) {
+            const int above = lane + o < 32 ? up[sw][o - 1] : (sw < 3 ? up[sw + 1][o - 1] : hhi[o - 1]);   // B[k + o]
+            hit |= av[sw] == above;
+        }
+        hits += hit ? 1 : 0;
+    }
+    return hits;
+}
+
+// Generic form of the windowed match for one candidate, whole warp (any max_dist, rows of any length): every lane
+// strides over A and looks B up in the +-max_dist window.  Returns this lane's share of |A n B|.
+__device__ __forceinline__ int verify_pair_windowed(const RowStore& m, int lane, int64_t ia, int la, int64_t ib, int lb, int max_dist) {
+    int inter = 0;
+    for (int k = lane; k < la; k += 32) {
+        const int x = row_col(m, ia, k);
+        bool hit = false;
+        for (int o = -max_dist; o <= max_dist; ++o) {
+            const int j = k + o;
+            if (j >= 0 && j < lb) hit |= (row_col(m, ib, j) == x);
+        }
+        inter += hit ? 1 : 0;
+    }
+    return inter;
+}
+
+// hooks the verified candidates of a warp's batch into the union-find and appends them to the edge list
+__device__ __forceinline__ void verify_emit(unsigned int edge_mask, int lane, int ra, int rb, int* __restrict__ parent,
+                                            uint2* __restrict__ edges, unsigned long long edge_cap, DevCounters* __restrict__ counters) {
+    const bool is_edge = (edge_mask >> lane) & 1u;
+    if (is_edge) uf_unite(parent, ra, rb);
+    if (edge_mask) {
+        unsigned long long pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&counters->n_edges, (unsigned long long)__popc(edge_mask));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (is_edge && edges) {
+            const unsigned long long pos = pos0 + __popc(edge_mask & ((1u << lane) - 1u));
+            if (pos < edge_cap) edges[pos] = make_uint2((uint32_t)min(ra, rb), (uint32_t)max(ra, rb));
+        }
+    }
+}
+
 template <int DWIN>
 __global__ void __launch_bounds__(256)
 k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
-               const int32_t* __restrict__ permB, const int64_t* __restrict__ indptr,
-               const int32_t* __restrict__ indices, int max_dist, int already_exact,
+               const int32_t* __restrict__ permB, const RowStore m, int max_dist, int already_exact,
                const unsigned char* __restrict__ is_query, int* __restrict__ parent, uint2* __restrict__ edges,
                unsigned long long edge_cap, DevCounters* __restrict__ counters) {
     const unsigned long long n = min(counters->n_cand, cand_cap);
@@ -1551,110 +1784,50 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
         unsigned int edge_mask = __ballot_sync(0xffffffffu, keep);
         if (!already_exact) {
             // row extents of all 32 candidates at once (one latency for the batch, not one per candidate)
-            int64_t my_ia = 0, my_la = 0, my_ib = 0, my_lb = 0;
+            int64_t my_ia = 0, my_ib = 0;
+            int my_la = 0, my_lb = 0;
             if (keep) {
-                my_ia = __ldg(&indptr[ra]);
-                my_la = __ldg(&indptr[ra + 1]) - my_ia;
-                my_ib = __ldg(&indptr[rb]);
-                my_lb = __ldg(&indptr[rb + 1]) - my_ib;
-                if (my_la > my_lb) { int64_t t = my_ia; my_ia = my_ib; my_ib = t; t = my_la; my_la = my_lb; my_lb = t; }
+                row_extent(m, ra, my_ia, my_la);
+                row_extent(m, rb, my_ib, my_lb);
+                if (my_la > my_lb) {   // A = the shorter row
+                    const int64_t t = my_ia; my_ia = my_ib; my_ib = t;
+                    const int tl = my_la; my_la = my_lb; my_lb = tl;
+                }
             }
-            unsigned int todo = edge_mask;
+            // a pair whose lengths differ by more than max_dist is further apart than that already
+            unsigned int todo = __ballot_sync(0xffffffffu, keep && my_lb - my_la <= max_dist);
             edge_mask = 0;
+            // Both rows ascend.  If |A xor B| <= max_dist, a common column sits at positions that differ by at most
+            // max_dist in the two rows (at most that many one-sided columns precede it), so matching A[k] against
+            // B[k-d..k+d] finds every common column; if the distance is larger the count can only be too small, i.e. the
+            // pair is still rejected.  No data-dependent addressing.
             while (todo) {
                 const int l = __ffs((int)todo) - 1;
                 todo &= todo - 1;
-                const int64_t ia = __shfl_sync(0xffffffffu, my_ia, l), la = __shfl_sync(0xffffffffu, my_la, l);
-                const int64_t ib = __shfl_sync(0xffffffffu, my_ib, l), lb = __shfl_sync(0xffffffffu, my_lb, l);
+                const int64_t ia = __shfl_sync(0xffffffffu, my_ia, l), ib = __shfl_sync(0xffffffffu, my_ib, l);
+                const int la = __shfl_sync(0xffffffffu, my_la, l), lb = __shfl_sync(0xffffffffu, my_lb, l);
                 int inter = 0;
-                if (lb - la <= (int64_t)max_dist) {  // otherwise d >= |lb - la| > max_dist already
-                    // Both rows ascend.  If |A xor B| <= max_dist, a common column sits at positions that
-                    // differ by at most max_dist in the two rows (at most that many one-sided columns
-                    // precede it), so matching A[k] against B[k-d..k+d] finds every common column; if the
-                    // distance is larger the count can only be too small, i.e. the pair is still rejected.
-                    // No data-dependent addressing.
-                    if (DWIN > 0) {
-                        // The rows are worked through in chunks of 128 columns (one chunk for nearly all rows): each lane
-                        // loads its <= 4 columns of either row once (positions base + lane + 32 s; all loads of a chunk
-                        // independent and issued back to back, so a chunk costs about one memory round trip) and gets the
-                        // +-DWIN neighbours of B from lane rotations instead of more loads; the DWIN columns of B just
-                        // outside the chunk come from two small halo loads.  (Equalising the batches over the warps - 26
-                        // candidates in each of three rounds instead of 32/32/0-or-32 at 1 M rows - was measured slower,
-                        // 289 vs 238 us: the scattered row reads run at about 2.4 TB/s and more warps in flight do not
-                        // raise that.)
-                        constexpr int NW = DWIN > 0 ? DWIN : 1;
-                        const int32_t* pa = indices + ia;
-                        const int32_t* pb = indices + ib;
-                        const int la32 = (int)la, lb32 = (int)lb;   // a row has fewer than 2^31 columns
-                        for (int base = 0; base < la32; base += 128) {
-                            int av[4], bv[4];
-#pragma unroll
-                            for (int sw = 0; sw < 4; ++sw) {
-                                const int k = base + lane + 32 * sw;
-                                av[sw] = k < la32 ? __ldg(pa + k) : -2;   // column ids are >= 0: the fillers match nothing
-                                bv[sw] = k < lb32 ? __ldg(pb + k) : -1;
-                            }
-                            // halo: lane t < NW holds B[base - NW + t] and B[base + 128 + t]
-                            int halo_lo = -1, halo_hi = -1;
-                            if (lane < NW) {
-                                if (base - NW + lane >= 0) halo_lo = __ldg(pb + base - NW + lane);
-                                if (base + 128 + lane < lb32) halo_hi = __ldg(pb + base + 128 + lane);
-                            }
-                            int dn[4][NW], up[4][NW];   // bv[sw] rotated by -o / +o lanes
-#pragma unroll
-                            for (int sw = 0; sw < 4; ++sw)
-#pragma unroll
-                                for (int o = 1; o <= NW; ++o) {
-                                    dn[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane - o) & 31);
-                                    up[sw][o - 1] = __shfl_sync(0xffffffffu, bv[sw], (lane + o) & 31);
-                                }
-                            // lane < o of the first sweep needs B[base + lane - o] = halo_lo of lane NW + lane - o;
-                            // lane >= 32 - o of the last sweep needs B[base + 128 + lane + o - 32] = halo_hi of that lane
-                            int hlo[NW], hhi[NW];
-#pragma unroll
-                            for (int o = 1; o <= NW; ++o) {
-                                hlo[o - 1] = __shfl_sync(0xffffffffu, halo_lo, (NW + lane - o) & 31);
-                                hhi[o - 1] = __shfl_sync(0xffffffffu, halo_hi, (lane + o) & 31);
-                            }
-#pragma unroll
-                            for (int sw = 0; sw < 4; ++sw) {
-                                bool hit = av[sw] == bv[sw];
-#pragma unroll
-                                for (int o = 1; o <= NW; ++o) {
-                                    const int below = lane >= o ? dn[sw][o - 1] : (sw > 0 ? dn[sw - 1][o - 1] : hlo[o - 1]);        // B[k - o]
-                                    const int above = lane + o < 32 ? up[sw][o - 1] : (sw < 3 ? up[sw + 1][o - 1] : hhi[o - 1]);   // B[k + o]
-                                    hit |= (av[sw] == below) | (av[sw] == above);
-                                }
-                                inter += hit ? 1 : 0;
-                            }
-                        }
-                    } else {
-                        for (int64_t k = lane; k < la; k += 32) {
-                            const int x = __ldg(&indices[ia + k]);
-                            bool hit = false;
-                            for (int o = -max_dist; o <= max_dist; ++o) {
-                                const int64_t j = k + o;
-                                if (j >= 0 && j < lb) hit |= (__ldg(&indices[ib + j]) == x);
-                            }
-                            inter += hit ? 1 : 0;
-                        }
+                if (DWIN > 0) {
+                    // The rows are worked through in chunks of 128 columns (one chunk for nearly all rows): each lane loads
+                    // its <= 4 columns of either row once (all loads of a chunk independent and issued back to back, so a
+                    // chunk costs about one memory round trip) and gets the +-DWIN neighbours of B from lane rotations
+                    // instead of more loads.  (Measured and dropped: equalising the batches over the warps, 289 vs 238 us;
+                    // requesting the next candidate's chunk before this one's is consumed, 208 vs 192 us - the extra
+                    // registers cost a resident block per SM.)
+                    constexpr int NW = DWIN > 0 ? DWIN : 1;
+                    int av[4], bv[4], halo_lo, halo_hi;
+                    for (int cbase = 0; cbase < la; cbase += 128) {
+                        verify_load_chunk<NW>(m, lane, cbase, ia, la, ib, lb, av, bv, halo_lo, halo_hi);
+                        inter += verify_match_chunk<NW>(lane, av, bv, halo_lo, halo_hi);
                     }
-                    inter = __reduce_add_sync(0xffffffffu, inter);
-                    if (la + lb - 2 * (int64_t)inter <= (int64_t)max_dist) edge_mask |= 1u << l;
+                } else {
+                    inter = verify_pair_windowed(m, lane, ia, la, ib, lb, max_dist);
                 }
+                inter = __reduce_add_sync(0xffffffffu, inter);
+                if ((int64_t)la + lb - 2 * (int64_t)inter <= (int64_t)max_dist) edge_mask |= 1u << l;
             }
         }
-        const bool is_edge = (edge_mask >> lane) & 1u;
-        if (is_edge) uf_unite(parent, ra, rb);
-        if (edge_mask) {
-            unsigned long long pos0 = 0;
-            if (lane == 0) pos0 = atomicAdd(&counters->n_edges, (unsigned long long)__popc(edge_mask));
-            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-            if (is_edge && edges) {
-                const unsigned long long pos = pos0 + __popc(edge_mask & ((1u << lane) - 1u));
-                if (pos < edge_cap) edges[pos] = make_uint2((uint32_t)min(ra, rb), (uint32_t)max(ra, rb));
-            }
-        }
+        verify_emit(edge_mask, lane, ra, rb, parent, edges, edge_cap, counters);
     }
 }
 
@@ -1664,6 +1837,41 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
 // other kernels read: a warp per row, 128-bit stores where the row start allows.  HBM: reads 2 nnz + 6 N bytes, writes
 // 4 nnz + 8 N bytes (the host link carries half of what the plain form needs).
 // ------------------------------------------------------------------------------------------
+// The opposite direction, once per uploaded matrix (bf_upload_csr): plain CSR -> compact resident form, so that every
+// pass over the matrix streams 2 bytes per column instead of 4.  A warp per row.  `bad` is raised if the matrix is not
+// representable after all (a column outside [0, 131072), a row that is not strictly ascending or has more than 65535
+// columns); the caller then keeps using the plain form.
+__global__ void __launch_bounds__(256) k_csr16_encode(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                      int64_t n, uint32_t* __restrict__ indptr32, uint16_t* __restrict__ split,
+                                                      uint16_t* __restrict__ lo, int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp0 * 32; r0 <= n; r0 += n_warps * 32) {
+        const int64_t r = r0 + lane;
+        int64_t my_b = 0, my_e = 0;
+        if (r <= n) {
+            my_b = __ldg(&indptr[r]);
+            indptr32[r] = (uint32_t)my_b;
+            my_e = r < n ? __ldg(&indptr[r + 1]) : my_b;
+        }
+        bool wrong = my_e - my_b > 65535;
+        for (int l = 0; l < 32 && r0 + l < n; ++l) {
+            const int64_t b = __shfl_sync(0xffffffffu, my_b, l), e = __shfl_sync(0xffffffffu, my_e, l);
+            uint32_t low = 0;
+            for (int64_t k = b + lane; k < e; k += 32) {
+                const int32_t col = __ldg(&indices[k]);
+                wrong |= (uint32_t)col >= 131072u || (k > b && __ldg(&indices[k - 1]) >= col);
+                low += (uint32_t)col < 65536u ? 1u : 0u;
+                lo[k] = (uint16_t)((uint32_t)col & 0xffffu);
+            }
+            low = __reduce_add_sync(0xffffffffu, low);
+            if (lane == 0) split[r0 + l] = (uint16_t)min(low, 65535u);
+        }
+        if (wrong) atomicOr(bad, 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_csr16_decode(const uint32_t* __restrict__ indptr32, const uint16_t* __restrict__ split,
                                                       const uint16_t* __restrict__ lo, int64_t n, int64_t* __restrict__ indptr,
                                                       int32_t* __restrict__ indices) {

@@ -107,6 +107,21 @@ def test_both_level1_kernels_are_exact(level1, max_dist):
         assert np.array_equal(ctx.download_labels(), want) and st.n_edges == ne
 
 
+@pytest.mark.parametrize("max_dist", [8, 9, 16, 32])
+@pytest.mark.parametrize("level1", [0, 1])
+@pytest.mark.parametrize("bits", [128, 256])
+def test_large_max_dist_where_the_32_bit_level_cannot_reject(bits, level1, max_dist):
+    """from max_dist 16 on the 32-bit level-1 test passes every pair (threshold 32 - 2 d <= 0) and the work falls to
+    level 2 and the verification (capacities are raised and the pass rerun where the queues overflow); 8 / 9 straddle
+    the switch from the three-key to the two-key schedule.  Still exact."""
+    indptr, indices, n_cols = synth.generate(1500, seed=17).csr()
+    want, ne = oracle.cluster(indptr, indices, max_dist)
+    with _native.Context(level1=level1, sketch_bits=bits) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols)
+        st = ctx.run_sync(max_dist)
+        assert np.array_equal(ctx.download_labels(), want) and st.n_edges == ne
+
+
 @pytest.mark.parametrize("bits", [128, 256, 512, 1024, 2048])
 def test_every_sketch_width_is_exact(bits):
     indptr, indices, n_cols = synth.generate(3000, seed=77).csr()
@@ -586,6 +601,92 @@ def test_compact_csr16_upload_gives_the_plain_answer(wide):
         for x in q:
             if x is not None:
                 lib.bf_pinned_free(x)
+
+
+def _run_ctx(indptr, indices, n_cols, max_dist, query_rows=None, **options):
+    with _native.Context(want_edges=1, **options) as ctx:
+        ctx.upload_csr(indptr, indices, n_cols, query_rows=query_rows)
+        st = ctx.run_sync(max_dist)
+        labels = ctx.download_labels()
+        src, dst = ctx.download_edges()
+    return labels, src, dst, st
+
+
+@pytest.mark.parametrize("shape", ["cols<=65536", "cols>65536", "cols>131072", "long_rows", "ragged"])
+@pytest.mark.parametrize("max_dist", [1, 2, 3, 5])
+def test_resident_compact_form_changes_nothing(shape, max_dist):
+    """bf_upload_csr derives the compact resident form (k_csr16_encode) and the sketch pass + verification then read it
+    (k_pack_sketch_rows16, k_verify_unite<., true>): same labels and edges as with the plain CSR (option resident_csr16
+    = 0) and as the oracle - also where the matrix is not representable and the plain form has to stay in charge"""
+    rng = np.random.default_rng(7 + max_dist)
+    if shape in ("cols<=65536", "cols>65536", "cols>131072"):
+        ip, ix, nc = synth.generate(6000, seed=31).csr()
+        target = {"cols<=65536": 65536, "cols>65536": 131072, "cols>131072": 400000}[shape]
+        ix = (ix.astype(np.int64) * (target - 1) // max(nc - 1, 1)).astype(np.int32)
+        nc = target
+    elif shape == "long_rows":
+        # 700 rows of about 600 columns: a block of 128 rows spans several staging chunks, rows span several
+        # verification chunks; clusters of near-identical rows
+        base = [np.sort(rng.choice(90000, size=600, replace=False)) for _ in range(70)]
+        rows = []
+        for b in base:
+            for _ in range(10):
+                r = set(b.tolist())
+                for _ in range(int(rng.integers(0, 3))):
+                    r ^= {int(rng.integers(0, 90000))}
+                rows.append(sorted(r))
+        ip, ix, nc = rows_to_csr(rows, 90000)
+    else:
+        big = list(range(0, 120000, 3))
+        rows = [big, big + [120001], [], [1], [1, 70000], big[:-1], [], list(range(65530, 65545)), list(range(65531, 65545)), [70000]]
+        ip, ix, nc = rows_to_csr(rows, 130000)
+    want_labels, _ = oracle.cluster(ip, ix, max_dist)
+    ws, wd = oracle.edges(ip, ix, max_dist)
+    for resident in (1, 0):
+        labels, src, dst, st = _run_ctx(ip, ix, nc, max_dist, resident_csr16=resident)
+        assert np.array_equal(labels, want_labels), resident
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd), resident
+
+
+def test_resident_compact_form_rectangle_and_unsorted_rows():
+    """query rows (the cache path's rectangle) on the compact form; a matrix whose rows are not ascending is refused by
+    the encoder and handled by the plain path exactly as before"""
+    ip, ix, nc = synth.generate(5000, seed=77).csr()
+    q = np.arange(0, 5000, 9, dtype=np.int32)
+    want = None
+    for resident in (1, 0):
+        labels, src, dst, _ = _run_ctx(ip, ix, nc, 2, query_rows=q, resident_csr16=resident)
+        if want is None:
+            want = (labels, src, dst)
+            ws, wd = oracle.edges(ip, ix, 2, queries=q)
+            assert np.array_equal(src, ws) and np.array_equal(dst, wd)
+        assert np.array_equal(labels, want[0]) and np.array_equal(src, want[1]) and np.array_equal(dst, want[2])
+    # descending rows: same answer with and without the option (the encoder flags the matrix, nothing changes)
+    ix2 = ix.copy()
+    for r in range(0, 50):
+        ix2[ip[r]:ip[r + 1]] = ix2[ip[r]:ip[r + 1]][::-1]
+    a = _run_ctx(ip, ix2, nc, 1, resident_csr16=1)
+    b = _run_ctx(ip, ix2, nc, 1, resident_csr16=0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("engine,options", [("hashjoin", {}), ("full", {}), ("sketch", {"sketch_bits": 512}), ("sketch", {"sketch_bits": 256})])
+def test_compact_upload_then_engines_that_want_the_plain_csr(engine, options):
+    """after bf_upload_csr16_async only the compact form is resident; engines and sketch widths whose kernels read the
+    plain CSR get it decoded inside bf_run"""
+    lib = _native.load()
+    ip, ix, nc = synth.generate(7000, seed=55).csr()
+    want, _ = oracle.cluster(ip, ix, 2)
+    ip32, split, lo = _native.csr16_encode(ip, ix, nc)
+    pins = [_pinned_copy(lib, ip32), _pinned_copy(lib, split) if split is not None else None, _pinned_copy(lib, lo)]
+    with _native.Context(engine=engine, **options) as ctx:
+        for _ in range(3):
+            ctx.upload_csr16_async_ptr(pins[0].value, pins[1].value if pins[1] is not None else None, pins[2].value, len(ip) - 1, nc)
+            ctx.run_sync(2)
+            assert np.array_equal(ctx.download_labels(), want)
+    for x in pins:
+        if x is not None:
+            lib.bf_pinned_free(x)
 
 
 def test_measured_pipe_peaks_are_plausible():
