@@ -431,7 +431,7 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
             uint32_t* f8a = nullptr;   // expanded row operand (fragment order) and column operand (row-major)
             uint4* f8b = nullptr;
             if (c->level1 == 1) {
-                for (int f = 0; f < 2; ++f) TRY(fold8[f].ensure((size_t)(tiles + L1_GROUP) * TILE * 32));  // + slack: a bulk copy never crosses the end
+                for (int f = 0; f < 2; ++f) TRY(fold8[f].ensure((size_t)(tiles + IMMA_GROUP) * TILE * 32));  // + slack: a bulk copy never crosses the end
                 f8a = fold8[0].as<uint32_t>();
                 f8b = fold8[1].as<uint4>();
             }
@@ -1123,8 +1123,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         TRY(c->jlo.ensure((size_t)n_entries * sizeof(int32_t)));
         TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
         TRY(c->jend.ensure((size_t)n_entries * sizeof(int32_t)));
-        const int group = c->ran_two_kernel ? L1_GROUP : 1;
-        k_schedule<<<grid_for(c->tilesA, 128), 128, 0, c->stream>>>(
+        const int group = c->ran_two_kernel ? (c->level1 == 1 ? IMMA_GROUP : L1_GROUP) : 1;
+        k_schedule<<<grid_for(c->tilesA, std::max(1, SCHED_THREADS / n_ranges)), SCHED_THREADS, 0, c->stream>>>(
             keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, c->has_query ? 0 : 1, group, n_keys, n_ranges,
             c->sched_table.as<SchedRange>(), n_keys == 3 ? c->sched_table_n : 0,
             c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),

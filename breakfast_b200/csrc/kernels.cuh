@@ -26,6 +26,7 @@
 // 32 lanes of a warp that read 32 consecutive rows at the same k4 read 512 contiguous bytes:
 // conflict-free 128-bit shared loads.
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -337,26 +338,41 @@ struct SchedRange {
     int8_t D, Ds, dt_min, dt_max;
 };
 
-__global__ void k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __restrict__ keysB,
+// One thread per schedule entry (row tile, range): its two binary searches over the tile ends of B are independent of
+// the other entries', so a block of SCHED_THREADS threads works on SCHED_THREADS / n_ranges row tiles at once and a
+// tile's entries cost one search latency instead of n_ranges of them (a thread per row tile: 27 us at 1 M rows and
+// max_dist 1; this form: see profiles/).  The clipping against the previous entry of the same tile (no B tile listed
+// twice) is a short sequential pass of the entry-0 thread over shared memory.
+constexpr int SCHED_THREADS = 256;
+__global__ void __launch_bounds__(SCHED_THREADS)
+k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __restrict__ keysB,
                            int64_t nB, int max_dist, int triangular, int group, int n_keys, int n_ranges,
                            const SchedRange* __restrict__ table3, int n_table3, int32_t* __restrict__ jlo,
                            int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
                            unsigned long long* __restrict__ n_tilepairs) {
+    __shared__ int32_t raw_first[SCHED_THREADS], raw_end[SCHED_THREADS];
+    __shared__ unsigned char raw_have[SCHED_THREADS];   // 0 = empty, 1 = range, 2 = the clamped group (listed once per tile)
     const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
-    int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (I >= tA) return;
-    const sortkey_t kMin = keysA[I * TILE], kMax = keysA[min(nA, (I + 1) * TILE) - 1];
+    const int tiles_per_block = max(1, SCHED_THREADS / n_ranges);   // n_ranges > SCHED_THREADS: a thread walks several entries
+    const int tl = threadIdx.x / n_ranges, r0 = threadIdx.x % n_ranges;
+    const int64_t I = (int64_t)blockIdx.x * tiles_per_block + tl;
+    const bool active = tl < tiles_per_block && I < tA;
+    sortkey_t kMin = 0, kMax = 0;
+    if (active) {
+        kMin = keysA[I * TILE];
+        kMax = keysA[min(nA, (I + 1) * TILE) - 1];
+    }
     const int64_t cMin = (int64_t)(kMin >> 32), cMax = (int64_t)(kMax >> 32);
     const int64_t sMin = (int64_t)((kMin >> 16) & 0xffffu), sMax = (int64_t)((kMax >> 16) & 0xffffu);
     const int64_t tMin = (int64_t)(kMin & 0xffffu), tMax = (int64_t)(kMax & 0xffffu);
     const bool single_c = n_keys >= 2 && cMin == cMax && cMax < (int64_t)KEY_CLAMP;
     const bool single_cs = n_keys >= 3 && single_c && sMin == sMax;
     const int n_gen = single_cs ? n_table3 : (single_c ? 2 * max_dist + 1 : 1);
-    int64_t prev_end = triangular ? I : 0;
-    unsigned long long tp_sum = 0, items_sum = 0;
-    bool clamp_done = false;
-    for (int r = 0; r < n_ranges; ++r) {
-        bool have = false;
+    // with n_ranges <= SCHED_THREADS a thread has exactly one entry (r = r0); otherwise the one tile of the block is
+    // walked by all threads in strides (its raw results do not fit shared memory: entry 0's thread redoes the chain
+    // below from global memory, see the second pass)
+    for (int r = r0; active && r < n_ranges; r += SCHED_THREADS) {
+        int have = 0;
         sortkey_t lo_key = 0, hi_key = 0;
         if (r < n_gen) {
             if (single_cs) {
@@ -364,15 +380,13 @@ __global__ void k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, cons
                 const int64_t c2 = cMin + e.D, s2 = sMin + e.Ds;
                 if (c2 >= 0 && c2 <= (int64_t)KEY_CLAMP) {
                     if (c2 == (int64_t)KEY_CLAMP) {   // the clamped group carries no s / t: listed once, as a whole
-                        if (!clamp_done) {
-                            have = clamp_done = true;
-                            lo_key = (sortkey_t)c2 << 32;
-                            hi_key = ((sortkey_t)c2 << 32) | 0xffffffffull;
-                        }
+                        have = 2;
+                        lo_key = (sortkey_t)c2 << 32;
+                        hi_key = ((sortkey_t)c2 << 32) | 0xffffffffull;
                     } else if (s2 >= 0) {
                         const int64_t t_lo = max((int64_t)0, tMin + e.dt_min), t_hi = min((int64_t)0xffff, tMax + e.dt_max);
                         if (t_lo <= t_hi) {
-                            have = true;
+                            have = 1;
                             lo_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s2 << 16) | (sortkey_t)t_lo;
                             hi_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s2 << 16) | (sortkey_t)t_hi;
                         }
@@ -386,39 +400,70 @@ __global__ void k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, cons
                         s_lo = max((int64_t)0, sMin - (max_dist - D) / 2);
                         s_hi = min((int64_t)0xffff, sMax + (D + max_dist) / 2);
                     }
-                    have = true;
+                    have = 1;
                     lo_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s_lo << 16);
                     hi_key = ((sortkey_t)c2 << 32) | ((sortkey_t)s_hi << 16) | 0xffffull;
                 }
             } else {
-                have = true;
+                have = 1;
                 lo_key = (sortkey_t)max((int64_t)0, cMin - max_dist) << 32;
                 hi_key = ((sortkey_t)min((int64_t)KEY_CLAMP, cMax + max_dist) << 32) | 0xffffffffull;
             }
         }
-        int64_t first = prev_end, end = prev_end;
+        int64_t first = 0, end = 0;
         if (have) {
-            // first J with bMax[J] >= lo_key
-            int64_t l = 0, rr = tB;
-            while (l < rr) {
-                const int64_t mid = (l + rr) >> 1;
-                const sortkey_t bMax = keysB[min(nB, (mid + 1) * TILE) - 1];
-                if (bMax >= lo_key) rr = mid; else l = mid + 1;
+            // first J with bMax[J] >= lo_key / first J with bMin[J] > hi_key: the two searches step together
+            int64_t l1 = 0, r1 = tB, l2 = 0, r2 = tB;
+            while (l1 < r1 || l2 < r2) {
+                const int64_t m1 = (l1 + r1) >> 1, m2 = (l2 + r2) >> 1;
+                const sortkey_t bMax = l1 < r1 ? keysB[min(nB, (m1 + 1) * TILE) - 1] : 0;
+                const sortkey_t bMin = l2 < r2 ? keysB[m2 * TILE] : 0;
+                if (l1 < r1) { if (bMax >= lo_key) r1 = m1; else l1 = m1 + 1; }
+                if (l2 < r2) { if (bMin > hi_key) r2 = m2; else l2 = m2 + 1; }
             }
-            first = l;
-            // first J with bMin[J] > hi_key
-            l = 0; rr = tB;
-            while (l < rr) {
-                const int64_t mid = (l + rr) >> 1;
-                const sortkey_t bMin = keysB[mid * TILE];
-                if (bMin > hi_key) rr = mid; else l = mid + 1;
-            }
-            end = l;
+            first = l1;
+            end = l2;
+        }
+        if (n_ranges <= SCHED_THREADS) {
+            raw_first[threadIdx.x] = (int32_t)first;
+            raw_end[threadIdx.x] = (int32_t)end;
+            raw_have[threadIdx.x] = (unsigned char)have;
+        } else {   // parked in the output arrays, clipped below
+            jlo[I * n_ranges + r] = have ? (int32_t)first : -1 - have;
+            jend[I * n_ranges + r] = (int32_t)end | (have == 2 ? (int32_t)0x40000000 : 0);
+        }
+    }
+    __syncthreads();
+    if (!active || r0 != 0) return;
+    // second pass, entry 0's thread: clip every range against the end of the previous one
+    int64_t prev_end = triangular ? I : 0;
+    unsigned long long tp_sum = 0, items_sum = 0;
+    bool clamp_done = false;
+    for (int r = 0; r < n_ranges; ++r) {
+        int have;
+        int64_t first, end;
+        const int64_t e = I * n_ranges + r;
+        if (n_ranges <= SCHED_THREADS) {
+            have = raw_have[threadIdx.x + r];
+            first = raw_first[threadIdx.x + r];
+            end = raw_end[threadIdx.x + r];
+        } else {
+            const int32_t f = jlo[e], en = jend[e];
+            have = f < 0 ? 0 : ((en & 0x40000000) ? 2 : 1);
+            first = f;
+            end = en & 0x3fffffff;
+        }
+        if (have == 2) {
+            if (clamp_done) have = 0;
+            clamp_done = true;
+        }
+        if (have) {
             first = max(first, prev_end);
             end = max(end, first);
             prev_end = end;
+        } else {
+            first = end = prev_end;
         }
-        const int64_t e = I * n_ranges + r;
         jlo[e] = (int32_t)first;
         jend[e] = (int32_t)end;
         const unsigned long long tp = (unsigned long long)(end - first);
@@ -865,7 +910,7 @@ __global__ void __launch_bounds__(256) k_pack_full(const int64_t* __restrict__ i
 // K2c: explicit work list.  items[w] = (I, J) for every band tile pair, so that the pair kernel's
 // producer needs one load per item instead of a binary search.
 // ------------------------------------------------------------------------------------------
-// With group > 1 an item covers column tiles J0 .. J0+cnt-1 (cnt <= group <= 4) and is stored as
+// With group > 1 an item covers column tiles J0 .. J0+cnt-1 (cnt <= group <= 8) and is stored as
 // (I, J0 | (cnt-1) << 29); jcount[I] (tile pairs of row tile I) is recomputed from the next prefix.
 // work item w of row tile I (wprefix[I] <= w < wprefix[I + 1]) -> (first column tile, number of column tiles):
 // walk the tile's n_ranges schedule entries
@@ -1238,11 +1283,12 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
 // against ~27 pairs/clk/SM of the integer-pipe level 1; a tcgen05/TMEM variant was bit-exact but slower
 // (accumulator round-trip latency with K = 32, see tools/experiments/l1_tcgen05_kernel.cuh.txt).
 // ------------------------------------------------------------------------------------------
-constexpr int IMMA_STAGES = 6;
+constexpr int IMMA_STAGES = 5;
+constexpr int IMMA_GROUP = 8;    // column tiles per work item of the tensor-core level 1 (runs are six tiles long on average)
 constexpr int L2_CBUF = 1024;   // candidates a CTA of k_pairs_l2_unit collects per round before one cursor update
 constexpr int L2_SUB = 64;      // CTAs of k_pairs_l2_unit per queue segment (one unit per thread for segments up to 16 K units)
 constexpr int IMMA_TILE_BYTES = TILE * 32;
-constexpr int IMMA_STAGE_BYTES = (1 + L1_GROUP) * IMMA_TILE_BYTES;
+constexpr int IMMA_STAGE_BYTES = (1 + IMMA_GROUP) * IMMA_TILE_BYTES;
 constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
 
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -1312,36 +1358,32 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
 
     const int thr = 32 - 2 * max_dist;
     const int frow = lane >> 2, fk = (lane & 3) * 8;   // B fragment: row inside the warp's 8 rows, byte offset of this lane's k slice
-    uint32_t it = 0;
-    for (unsigned long long w = first; w < W; w += stride, ++it) {
-        const uint32_t stage = it % IMMA_STAGES, ph = (it / IMMA_STAGES) & 1u;
+    uint32_t stage = 0, ph = 0;
+    const uint32_t W32 = (uint32_t)W, stride32 = (uint32_t)stride;   // the work list holds at most 2^24 items
+    for (uint32_t w = (uint32_t)first; w < W32; w += stride32) {
         mbar_wait(&full_bar[stage], ph);
         const unsigned char* sA = smem + stage * IMMA_STAGE_BYTES;
-        const unsigned char* sB = sA + IMMA_TILE_BYTES;
+        const unsigned char* sB = sA + IMMA_TILE_BYTES + (8 * warp + frow) * 32 + fk;
         const int2 ij = meta[stage];
         const int cnt = ((unsigned)ij.y >> 29) + 1;
         // A fragments of the 8 m-tiles, stored in fragment order by the pack kernel: one LDS.128 each
         uint4 a[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) a[m] = reinterpret_cast<const uint4*>(sA)[m * 32 + lane];
-        // The four column tiles of an item are unrolled (missing ones predicated off): all B fragments are
-        // loaded up front and the MMAs are issued in groups of four m-tiles, so that the max tree of one group
-        // overlaps the tensor-pipe time of the next (software pipeline across the half-groups).
-        uint2 b[L1_GROUP];
+        // The column tiles of an item are unrolled (missing ones skipped, warp-uniformly): per tile one LDS.64 and the
+        // MMAs in two groups of four m-tiles, so that the max tree of one group overlaps the tensor-pipe time of the next.
+        int mxj[IMMA_GROUP];
 #pragma unroll
-        for (int jt = 0; jt < L1_GROUP; ++jt)
-            b[jt] = *reinterpret_cast<const uint2*>(sB + (jt < cnt ? jt : 0) * IMMA_TILE_BYTES + (8 * warp + frow) * 32 + fk);
-        int mxj[L1_GROUP];
-#pragma unroll
-        for (int jt = 0; jt < L1_GROUP; ++jt) {
-            mxj[jt] = -64;
-            if (jt >= cnt) continue;   // warp-uniform: a partly filled item does not pay for its missing tiles
+        for (int jt = 0; jt < IMMA_GROUP; ++jt) {
+            mxj[jt] = INT_MIN;   // below any threshold
+            if (jt >= cnt) continue;   // a partly filled item does not pay for its missing tiles
+            const uint2 b = *reinterpret_cast<const uint2*>(sB + jt * IMMA_TILE_BYTES);
             int mh[2];
 #pragma unroll
             for (int hgrp = 0; hgrp < 2; ++hgrp) {
                 int c[4][4];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) imma_16832(c[m], a[4 * hgrp + m], b[jt].x, b[jt].y);
+                for (int m = 0; m < 4; ++m) imma_16832(c[m], a[4 * hgrp + m], b.x, b.y);
                 int m0 = max(max(c[0][0], c[0][1]), max(c[0][2], c[0][3]));
                 int m1 = max(max(c[1][0], c[1][1]), max(c[1][2], c[1][3]));
                 m0 = max(m0, max(c[2][0], c[2][1]));
@@ -1352,17 +1394,26 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
             }
             mxj[jt] = max(mh[0], mh[1]);
         }
+        // rare: one of this lane's 16 x 2 pairs of tile pair (I, J0 + jt) may be within max_dist -> the unit goes to this
+        // CTA's segment of the level-2 queue (shared-memory cursor: no contended global atomic); one test for the item first
+        int any = mxj[0];
 #pragma unroll
-        for (int jt = 0; jt < L1_GROUP; ++jt) {
-            // rare: one of this lane's 16 x 2 pairs of tile pair (I, J0 + jt) may be within max_dist -> the unit goes
-            // to this CTA's segment of the level-2 queue (shared-memory cursor: no contended global atomic)
-            if (jt < cnt && mxj[jt] >= thr) {
-                const unsigned pos = atomicAdd(&seg_cursor, 1u);
-                if (pos < seg_cap) seg[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+        for (int jt = 1; jt < IMMA_GROUP; ++jt) any = max(any, mxj[jt]);
+        if (any >= thr) {
+#pragma unroll
+            for (int jt = 0; jt < IMMA_GROUP; ++jt) {
+                if (mxj[jt] >= thr) {
+                    const unsigned pos = atomicAdd(&seg_cursor, 1u);
+                    if (pos < seg_cap) seg[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+                }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == IMMA_STAGES) {
+            stage = 0;
+            ph ^= 1u;
+        }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(PAIR_CONSUMER_WARPS * 32) : "memory");   // consumer warps only
     if (threadIdx.x == 0) {
