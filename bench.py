@@ -262,7 +262,9 @@ def main():
     ap.add_argument("--sketch-bits", type=int, default=int(os.environ.get("BREAKFAST_B200_SKETCH_BITS", "128")))
     ap.add_argument("--engine", default="sketch", choices=["sketch", "full", "hashjoin"])
     ap.add_argument("--two-level", type=int, default=1, choices=[0, 1])
-    ap.add_argument("--level1", type=int, default=1, choices=[0, 1], help="1 = int8 mma.sync level 1 (default), 0 = integer pipes")
+    ap.add_argument("--level1", type=int, default=2, choices=[0, 1, 2],
+                    help="2 = int8 mma.sync level 1 with two column rows per accumulator (default), 1 = one row per accumulator, 0 = integer pipes")
+    ap.add_argument("--l1-ctas", type=int, default=0, choices=[0, 1, 2], help="CTAs per SM of the level-1 kernel (0 = library default)")
     ap.add_argument("--profiles", type=int, default=N_PROFILES, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip configs_ms / cli_wall_s / full-engine roofline (N = 1 extras)")
@@ -335,7 +337,7 @@ def main():
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     ctx = _native.Context(device=local_rank, stream=stream, engine=args.engine, sketch_bits=args.sketch_bits,
-                          two_level=args.two_level, level1=args.level1)
+                          two_level=args.two_level, level1=args.level1, l1_ctas=args.l1_ctas)
     ctx.upload_csr_ptr(p_indptr.value, p_indices.value, n, n_cols)
     runner = RankRunner(ctx, n, rank, world)   # N > 1: joins the library's own NCCL communicator (NCCL may print its banner on stdout)
 
@@ -370,7 +372,29 @@ def main():
     runs = max(1, min(st.runs_since_sync, 128))
     ms_pairs = st.ms_pairs_sum / runs
     two_kernel = args.engine == "sketch" and args.two_level and st.bits_per_row in (128, 256)
-    if two_kernel and args.level1 == 1:
+    if two_kernel and args.level1 == 2:
+        # dominant kernel = k_pairs_l1_imma2: the column operand packs two rows per int8 row (e1 + 64 e2), so one m16n8k32
+        # MMA decides 256 pairs: 16 executed int8 MACs per evaluated pair for the 32 MACs of the plain contraction
+        # (DESIGN.md section 3).  `achieved` counts the ALGORITHMIC 32 MACs per pair (2 F int8 ops per
+        # evaluated entry, F = 32 fold bits), `frac_executed` the MACs the tensor pipe really performs.
+        ms_kernel = st.ms_l1_sum / runs
+        kernel_name = f"k_pairs_l1_imma2 (int8 mma.sync, two column rows per accumulator, 32-bit folds of {st.bits_per_row}-bit sketches)"
+        bound, unit_r, peak = "tensor", "Gint8-MAC/s (mma.sync m16n8k32)", peaks["imma_s8"]
+        ops_per_launch = int(st.pairs_evaluated * 32)
+        achieved = ops_per_launch / (ms_kernel * 1e-3) / 1e9
+        sm_hz = 148 * 1.965e9
+        extra = {"macs_per_pair": 32, "executed_macs_per_pair": 16, "frac_executed": achieved / 2 / peak,
+                 "pairs_per_clk_per_sm": st.pairs_evaluated / (ms_kernel * 1e-3) / sm_hz,
+                 "level2_units": st.l2_warp_items, "ms_level2": (st.ms_pairs_sum - st.ms_l1_sum) / runs,
+                 "tcgen05_int8_peak": peaks["umma_i8"], "frac_of_tcgen05_int8_peak": achieved / peaks["umma_i8"],
+                 "note": "frac = algorithmic MACs (32 per evaluated pair) over the int8 rate reachable with register accumulators "
+                         "(mma.sync), frac_executed = the MACs really issued (16 per pair: two column rows share an accumulator); "
+                         "per pair the kernel also issues half an IMAD and a quarter of a packed 16x2 max, which is what binds "
+                         "next (ncu under profiles/).  frac_of_tcgen05_int8_peak = against the tcgen05.mma kind::i8 rate measured "
+                         "in this process; the tcgen05 form of this filter was built and instrumented twice "
+                         "(profiles/r02_tcgen05_*.log): one TMEM -> register read per pair and >= 1000 cycles per accumulator "
+                         "round trip cap it at 12-18 pairs/clk/SM"}
+    elif two_kernel and args.level1 == 1:
         # dominant kernel = k_pairs_l1_imma: one m16n8k32 int8 MMA per 128 pairs = 32 int8 MACs per evaluated pair
         # (DESIGN.md section 3); bound = the tensor pipe as reachable through mma.sync, peak measured in this process
         ms_kernel = st.ms_l1_sum / runs
@@ -426,7 +450,7 @@ def main():
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            key = (("k_pairs_l1_imma" if args.level1 == 1 else "k_pairs_l1") if two_kernel else "k_pairs") + \
+            key = (("k_pairs_l1_imma2" if args.level1 == 2 else "k_pairs_l1_imma" if args.level1 == 1 else "k_pairs_l1") if two_kernel else "k_pairs") + \
                 f"_{args.engine}_{st.bits_per_row}_n{n}_w{world}"
             traffic = json.loads(tf.read_text()).get(key)
         except Exception:
@@ -509,7 +533,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD if n == N_PROFILES else f"{n} profiles (override)", "max_dist": MAX_DIST,
-                       "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level), "level1": "imma" if args.level1 == 1 else "int_pipes",
+                       "engine": args.engine, "bits_per_row": st.bits_per_row, "two_level": bool(args.two_level), "level1": {2: "imma_packed_pairs", 1: "imma", 0: "int_pipes"}[args.level1],
                        "l2_warp_items": st.l2_warp_items, "pairs_evaluated": st.pairs_evaluated, "n_cols": n_cols, "nnz": int(indices.size),
                        "candidate_pairs": st.pairs_band, "pairs_total": st.pairs_total, "tiles_band": st.tiles_band,
                        "edges": None if world > 1 else st.n_edges, "components": st.n_components, "sketch_survivors_rank0": st.n_candidates,

@@ -89,7 +89,9 @@ int cuda_fail(cudaError_t e, const char* what, int line) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__);   \
     } while (0)
 #define CKL() CK(cudaGetLastError())
-#define CKLC(c) do { CK(cudaGetLastError()); ++(c)->launches_since_sync; } while (0)
+// BF_TRACE_KERNELS=1 (diagnostics): an event after every launch of a pass; bf_sync prints the in-situ timeline of the
+// last pass (api.cu line of the launch, microseconds since the previous mark) on stderr
+#define CKLC(c) do { CK(cudaGetLastError()); ++(c)->launches_since_sync; trace_mark((c), __LINE__); } while (0)
 #define TRY(expr)                    \
     do {                             \
         int rc_ = (expr);            \
@@ -145,6 +147,9 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64
 
 }  // namespace
 
+struct bf_ctx;
+static void trace_mark(bf_ctx* c, int line);
+
 struct bf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -158,7 +163,10 @@ struct bf_ctx {
     int64_t cand_capacity = 0;  // 0 = auto
     int blocks_per_sm = 0;      // 0 = occupancy
     int two_level = 1;
-    int level1 = 1;             // 1 = tensor cores (k_pairs_l1_imma, default), 0 = integer pipes (k_pairs_l1)
+    int level1 = 2;             // 2 = tensor cores, two column rows per accumulator (k_pairs_l1_imma2, default),
+                                // 1 = tensor cores (k_pairs_l1_imma), 0 = integer pipes (k_pairs_l1)
+    int l1_ctas = 0;            // CTAs per SM of k_pairs_l1_imma2 (1 or 2; 0 = the default, kL1CtasDefault)
+    int l1_segs = 0;            // segments of the level-2 queue of the last pass (= the grid of the tensor-core level 1)
     int64_t items_capacity = 0;  // 0 = auto
     int64_t units_capacity = 0;  // 0 = auto (level-2 queue)
 
@@ -199,6 +207,9 @@ struct bf_ctx {
     int pack16_variant = 1;   // one lane per row, ATOMS (fastest of the four, profiles/)
     int active_slot = -1;  // slot the current matrix lives in, -1 = caller-owned memory (bf_adopt_csr_device) or none
     bool use16 = false;    // this pass's sketch kernel reads the compact form
+    int verify16 = 0;      // option "verify_csr16" = 1: the exact verification reads its rows from the compact form too
+                           // (measured: 217 us against 170 us on the plain CSR at 10^6 profiles - half the bytes, but 16-bit
+                           // loads and the rebuilt 17th bit cost more than the bytes save; kept as an option)
     DevBuf hj_hash, hj_t1, hj_t2, hj_t2_rows;        // hash-join engine: row hashes, row table, one-deletion table
     const int64_t* d_indptr = nullptr;
     const int32_t* d_indices = nullptr;
@@ -222,7 +233,40 @@ struct bf_ctx {
     cudaEvent_t ring[kRing][5] = {};  // pass start, pairs start, pairs end, pass end, level-1 end
     int64_t runs_since_sync = 0;
     int64_t launches_since_sync = 0;
+    // BF_TRACE_KERNELS diagnostics
+    int trace = -1;   // -1 = environment not read yet
+    std::vector<cudaEvent_t> trace_ev;
+    std::vector<int> trace_line;
+    size_t trace_n = 0;
 };
+
+static void trace_mark(bf_ctx* c, int line) {
+    if (c->trace < 0) {
+        const char* e = getenv("BF_TRACE_KERNELS");
+        c->trace = (e && *e && *e != '0') ? 1 : 0;
+    }
+    if (!c->trace) return;
+    if (c->trace_n == c->trace_ev.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        c->trace_ev.push_back(ev);
+        c->trace_line.push_back(0);
+    }
+    c->trace_line[c->trace_n] = line;
+    cudaEventRecord(c->trace_ev[c->trace_n++], c->stream);
+}
+static void trace_dump(bf_ctx* c) {
+    if (c->trace != 1 || c->trace_n < 2) return;
+    float total = 0;
+    for (size_t i = 1; i < c->trace_n; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->trace_ev[i - 1], c->trace_ev[i]) == cudaSuccess) {
+            fprintf(stderr, "[bf trace] api.cu:%-5d %9.1f us\n", c->trace_line[i], ms * 1e3f);
+            total += ms;
+        }
+    }
+    fprintf(stderr, "[bf trace] total %.1f us over %zu marks\n", total * 1e3f, c->trace_n);
+}
 
 namespace {
 
@@ -418,7 +462,7 @@ int exchange_labels(bf_ctx* c) {
     return BF_OK;
 }
 
-int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBuf folds[2], DevBuf fold8[2]) {
+int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBuf folds[2], DevBuf fold8[2], int* parent_init) {
     if (n == 0) return BF_OK;
     const int64_t tiles = ceil_div(n, TILE);
     const size_t bytes = (size_t)tiles * c->n_chunks * c->K4 * TILE * 16;
@@ -430,16 +474,16 @@ int pack_rows(bf_ctx* c, const int32_t* perm_dev, int64_t n, DevBuf& bits, DevBu
             for (int f = 0; f < 2; ++f) TRY(folds[f].ensure((size_t)tiles * TILE * sizeof(uint32_t)));
             uint32_t* f8a = nullptr;   // expanded row operand (fragment order) and column operand (row-major)
             uint4* f8b = nullptr;
-            if (c->level1 == 1) {
+            if (c->level1 >= 1) {
                 for (int f = 0; f < 2; ++f) TRY(fold8[f].ensure((size_t)(tiles + IMMA_GROUP) * TILE * 32));  // + slack: a bulk copy never crosses the end
                 f8a = fold8[0].as<uint32_t>();
                 f8b = fold8[1].as<uint4>();
             }
             uint32_t *b32 = bits.as<uint32_t>(), *fo0 = folds[0].as<uint32_t>(), *fo1 = folds[1].as<uint32_t>();
             if (c->sketch_bits == 128)
-                k_permute_store<4><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b);
+                k_permute_store<4><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b, c->level1 == 2, parent_init);
             else
-                k_permute_store<8><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b);
+                k_permute_store<8><<<(unsigned)tiles, TILE, 0, c->stream>>>(c->sk_rows.as<uint32_t>(), perm_dev, n, b32, fo0, fo1, f8a, f8b, c->level1 == 2, parent_init);
         } else {
             const size_t smem = (size_t)c->n_chunks * c->K4 * TILE * 16;
             k_pack_sketch<<<(unsigned)tiles, 256, smem, c->stream>>>(c->d_indptr, c->d_indices, perm_dev, n, log2m,
@@ -489,24 +533,50 @@ int dispatch_pairs(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_
 }
 
 // level 1 on the tensor cores (mma.sync int8 on the +-1 expanded folds) + level 2 on the queue
-int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
+constexpr int kL1CtasDefault = 2;
+template <int MINB>
+int launch_imma2(bf_ctx* c, const uint32_t* f8a, const uint4* f8p, int64_t nA, int64_t nB, int tri) {
+    using Cfg = Imma2Cfg<MINB>;
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
-        CK(cudaFuncSetAttribute(k_pairs_l1_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, IMMA_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_pairs_l1_imma2<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set[c->device & 63] = true;
     }
+    k_pairs_l1_imma2<MINB><<<(unsigned)c->l1_segs, PAIR_THREADS, Cfg::kSmemBytes, c->stream>>>(
+        f8a, f8p, nA, nB, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, tri,
+        c->rank, c->world, 66560, 63 * 66560, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(), c->counters.as<DevCounters>());
+    CKLC(c);
+    return BF_OK;
+}
+
+int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
     const uint32_t* f8a = (c->has_query ? c->fold8A[0] : c->fold8B[0]).as<uint32_t>();
     const uint4* f8b = c->fold8B[1].as<uint4>();
-    k_pairs_l1_imma<<<(unsigned)c->num_sms, PAIR_THREADS, IMMA_SMEM_BYTES, c->stream>>>(
-        f8a, f8b, nA, nB, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, tri,
-        c->rank, c->world, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(), c->counters.as<DevCounters>());
-    CKLC(c);
+    const bool packed = c->level1 == 2;
+    const int ctas = packed ? (c->l1_ctas > 0 ? c->l1_ctas : kL1CtasDefault) : 1;
+    c->l1_segs = c->num_sms * ctas;
+    TRY(c->segcnt.ensure((size_t)c->l1_segs * sizeof(unsigned)));
+    if (packed) {
+        if (ctas == 2) TRY(launch_imma2<2>(c, f8a, f8b, nA, nB, tri));
+        else TRY(launch_imma2<1>(c, f8a, f8b, nA, nB, tri));
+    } else {
+        static bool attr_set[64] = {};
+        if (!attr_set[c->device & 63]) {
+            CK(cudaFuncSetAttribute(k_pairs_l1_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, IMMA_SMEM_BYTES));
+            attr_set[c->device & 63] = true;
+        }
+        k_pairs_l1_imma<<<(unsigned)c->l1_segs, PAIR_THREADS, IMMA_SMEM_BYTES, c->stream>>>(
+            f8a, f8b, nA, nB, c->items.as<int2>(), c->items_cap_used, c->nwork.as<unsigned long long>(), c->max_dist, tri,
+            c->rank, c->world, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(), c->counters.as<DevCounters>());
+        CKLC(c);
+    }
     CK(cudaEventRecord(c->ring[c->runs_since_sync % bf_ctx::kRing][4], c->stream));
     const uint4* fa = (c->has_query ? c->foldsA[0] : c->foldsB[0]).as<uint4>();
     const uint2* fb = c->foldsB[1].as<uint2>();
-    auto l2 = c->K4 == 1 ? k_pairs_l2_unit<1> : k_pairs_l2_unit<2>;
-    l2<<<c->num_sms * L2_SUB, 256, 0, c->stream>>>(A, B, fa, fb, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(),
-                                                  c->num_sms, c->max_dist, tri, c->cand.as<uint2>(), c->cand_cap_used,
+    auto l2 = packed ? (c->K4 == 1 ? k_pairs_l2_unit<1, true> : k_pairs_l2_unit<2, true>)
+                     : (c->K4 == 1 ? k_pairs_l2_unit<1, false> : k_pairs_l2_unit<2, false>);
+    l2<<<c->l1_segs * L2_SUB, 256, 0, c->stream>>>(A, B, fa, fb, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(),
+                                                  c->l1_segs, c->max_dist, tri, c->cand.as<uint2>(), c->cand_cap_used,
                                                   c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
@@ -514,7 +584,7 @@ int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA
 
 // level 1 on the fold planes (persistent, one CTA per SM) + level 2 on the queue
 int launch_two_kernel(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA, int64_t nB, int tri) {
-    if (c->level1 == 1) return launch_two_kernel_imma(c, A, B, nA, nB, tri);
+    if (c->level1 >= 1) return launch_two_kernel_imma(c, A, B, nA, nB, tri);
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
         CK(cudaFuncSetAttribute(k_pairs_l1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM_BYTES));
@@ -715,6 +785,7 @@ void bf_ctx_destroy(bf_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_aux) if (e) cudaEventDestroy(e);
+    for (auto& e : c->trace_ev) cudaEventDestroy(e);
     for (auto& r : c->ring) for (auto& e : r) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_upload_start) cudaEventDestroy(c->ev_upload_start);
@@ -746,8 +817,11 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
         if (value < 0) return fail(BF_ERR_INVALID, "items_capacity must be >= 0");
         c->items_capacity = value;
     } else if (k == "level1") {
-        if (value != 0 && value != 1) return fail(BF_ERR_INVALID, "level1 must be 0 (integer pipes) or 1 (tensor cores)");
+        if (value < 0 || value > 2) return fail(BF_ERR_INVALID, "level1 must be 0 (integer pipes), 1 (tensor cores) or 2 (tensor cores, two column rows per accumulator)");
         c->level1 = (int)value;
+    } else if (k == "l1_ctas") {
+        if (value < 0 || value > 2) return fail(BF_ERR_INVALID, "l1_ctas must be 0 (default), 1 or 2");
+        c->l1_ctas = (int)value;
     } else if (k == "merge_capacity") {
         if (value < 0) return fail(BF_ERR_INVALID, "merge_capacity must be >= 0");
         c->merge_capacity = value;
@@ -759,6 +833,8 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
         c->pack16_variant = (int)value;
     } else if (k == "resident_csr16") {
         c->resident16 = value ? 1 : 0;   // 0: the sketch pass streams the plain CSR
+    } else if (k == "verify_csr16") {
+        c->verify16 = value ? 1 : 0;
     } else if (k == "blocks_per_sm") {
         if (value < 0 || value > 8) return fail(BF_ERR_INVALID, "blocks_per_sm must be in [0, 8]");
         c->blocks_per_sm = (int)value;
@@ -1044,18 +1120,22 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     c->ran_two_level = !c->ran_two_kernel && c->engine == BF_ENGINE_SKETCH && c->n_chunks == 1 && c->two_level;
 
     cudaEvent_t* ring = c->ring[c->runs_since_sync % bf_ctx::kRing];
+    c->trace_n = 0;
+    trace_mark(c, __LINE__);
     CK(cudaEventRecord(c->ev[0], c->stream));
     CK(cudaEventRecord(ring[0], c->stream));
     CK(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), c->stream));
     CK(cudaMemsetAsync(c->nwork.p, 0, sizeof(unsigned long long), c->stream));
     TRY(c->parent.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int)));
     TRY(c->labels.ensure((size_t)std::max<int64_t>(nB, 1) * sizeof(int32_t)));
-    if (nB > 0) {
+    const bool active = nA > 0 && nB > 0;
+    // the staged pack of the B side (k_permute_store, one thread per row) initialises the union-find as well
+    const bool init_in_pack = active && c->engine == BF_ENGINE_SKETCH && staged_pack(c);
+    if (nB > 0 && !init_in_pack) {
         k_uf_init<<<grid_for(nB, 256), 256, 0, c->stream>>>(c->parent.as<int>(), nB);
         CKLC(c);
     }
 
-    const bool active = nA > 0 && nB > 0;
     DevBuf* keysA = c->has_query ? c->keysA : c->keysB;
     DevBuf* valsA = c->has_query ? c->valsA : c->valsB;
     if (active) {
@@ -1094,8 +1174,8 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     }
     if (active && !hashjoin) {
         // ---- K1: bit-pack
-        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB, c->fold8B));
-        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA, c->fold8A));
+        TRY(pack_rows(c, c->valsB[0].as<int32_t>(), nB, c->bitsB, c->foldsB, c->fold8B, init_in_pack ? c->parent.as<int>() : nullptr));
+        if (c->has_query) TRY(pack_rows(c, c->valsA[0].as<int32_t>(), nA, c->bitsA, c->foldsA, c->fold8A, nullptr));
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
     if (active && hashjoin) {
@@ -1123,16 +1203,13 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
         TRY(c->jlo.ensure((size_t)n_entries * sizeof(int32_t)));
         TRY(c->wprefix.ensure((size_t)(c->tilesA + 1) * sizeof(unsigned long long)));
         TRY(c->jend.ensure((size_t)n_entries * sizeof(int32_t)));
-        const int group = c->ran_two_kernel ? (c->level1 == 1 ? IMMA_GROUP : L1_GROUP) : 1;
+        const int group = c->ran_two_kernel ? (c->level1 >= 1 ? IMMA_GROUP : L1_GROUP) : 1;
         k_schedule<<<grid_for(c->tilesA, std::max(1, SCHED_THREADS / n_ranges)), SCHED_THREADS, 0, c->stream>>>(
             keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist, c->has_query ? 0 : 1, group, n_keys, n_ranges,
             c->sched_table.as<SchedRange>(), n_keys == 3 ? c->sched_table_n : 0,
             c->jlo.as<int32_t>(), c->jend.as<int32_t>(), c->wprefix.as<unsigned long long>(),
-            &c->counters.as<DevCounters>()->n_tilepairs);
-        CKLC(c);
-        CK(cudaMemsetAsync(c->wprefix.as<unsigned long long>() + c->tilesA, 0, sizeof(unsigned long long), c->stream));
-        k_exclusive_scan<unsigned long long><<<1, 1024, 0, c->stream>>>(c->wprefix.as<unsigned long long>(), c->tilesA + 1, c->nwork.as<unsigned long long>(), nullptr, 0);
-        CKLC(c);
+            &c->counters.as<DevCounters>()->n_tilepairs, &c->counters.as<DevCounters>()->sched_done, c->nwork.as<unsigned long long>());
+        CKLC(c);   // (its last block also scans the item counts: wprefix and the item total are ready)
         TRY(band_statistic(c, keysA[0].as<sortkey_t>(), nA, c->keysB[0].as<sortkey_t>(), nB, max_dist));
         // explicit work list for the producer (bounded; items beyond it fall back to a binary search)
         {
@@ -1180,22 +1257,33 @@ int bf_run(bf_ctx* c, int32_t max_dist, int32_t rank, int32_t world) {
     CK(cudaEventRecord(ring[2], c->stream));
     if (active) {
         // ---- K3b: verify + hook
-        RowStore rows{};
         const int32_t* pA = hashjoin ? nullptr : valsA[0].as<int32_t>();
         const int32_t* pB = hashjoin ? nullptr : c->valsB[0].as<int32_t>();
         const unsigned char* isq = (c->has_query && !hashjoin) ? c->is_query.as<unsigned char>() : nullptr;
-        {
-            auto verify = k_verify_unite<0>;   // window = max_dist: a wider compile-time window would still be exact
-            if (max_dist == 1) verify = k_verify_unite<1>;
-            else if (max_dist == 2) verify = k_verify_unite<2>;
-            else if (max_dist == 3) verify = k_verify_unite<3>;
-            rows.indptr = c->d_indptr;
-            rows.indices = c->d_indices;
+        // rows from the compact resident form where the slot holds it (half the bytes per column), else the plain CSR
+        const bool rows16 = c->verify16 && c->resident16 && c->active_slot >= 0 && c->c16_valid[c->cur];
+        auto launch_verify = [&](auto kernel, auto rows) -> int {
             int vbps = 0;   // grid-stride kernel: launch exactly the blocks that are resident at once
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, verify, 256, 0));
-            verify<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vbps, kernel, 256, 0));
+            kernel<<<c->num_sms * std::max(1, vbps), 256, 0, c->stream>>>(
                 c->cand.as<uint2>(), c->cand_cap_used, pA, pB, rows, max_dist, c->engine == BF_ENGINE_FULL ? 1 : 0, isq,
                 c->parent.as<int>(), c->want_edges ? c->edges.as<uint2>() : nullptr, c->cand_cap_used, c->counters.as<DevCounters>());
+            return BF_OK;
+        };
+        // window = max_dist: a wider compile-time window would still be exact
+        if (rows16) {
+            const RowStore16 rows{c->c16_indptr[c->cur].as<uint32_t>(),
+                                  c->c16_has_split[c->cur] ? c->c16_split[c->cur].as<uint16_t>() : nullptr, c->c16_lo[c->cur].as<uint16_t>()};
+            if (max_dist == 1) TRY(launch_verify(k_verify_unite<1, RowStore16>, rows));
+            else if (max_dist == 2) TRY(launch_verify(k_verify_unite<2, RowStore16>, rows));
+            else if (max_dist == 3) TRY(launch_verify(k_verify_unite<3, RowStore16>, rows));
+            else TRY(launch_verify(k_verify_unite<0, RowStore16>, rows));
+        } else {
+            const RowStore rows{c->d_indptr, c->d_indices};
+            if (max_dist == 1) TRY(launch_verify(k_verify_unite<1, RowStore>, rows));
+            else if (max_dist == 2) TRY(launch_verify(k_verify_unite<2, RowStore>, rows));
+            else if (max_dist == 3) TRY(launch_verify(k_verify_unite<3, RowStore>, rows));
+            else TRY(launch_verify(k_verify_unite<0, RowStore>, rows));
         }
         CKLC(c);
     }
@@ -1358,6 +1446,7 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
     if (!c->ran) return fail(BF_ERR_STATE, "bf_sync before bf_run");
     TRY(set_device(c));
     CK(cudaStreamSynchronize(c->stream));
+    trace_dump(c);
     DevCounters h;
     unsigned long long nwork = 0;
     CK(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
@@ -1393,7 +1482,7 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
                 // level 1: one 32-bit test per pair, half of them by POPC when max_dist is 1 or 2 (the other
                 // half runs POPC-free on the ALU/FMA pipes); level 2: `words` POPC per pair of every queued 32-pair unit
                 st->l2_warp_items = (int64_t)std::min<unsigned long long>(h.n_units, c->queue_cap_used);
-                if (c->level1 == 1) {  // tensor-core level 1: no POPC there; level 2 = the exact 32-bit test of a unit's
+                if (c->level1 >= 1) {  // tensor-core level 1: no POPC there; level 2 = the exact 32-bit test of a unit's
                                        // 32 pairs + `words` POPC for every pair that passes it (counted on the device)
                     st->popc32_executed = st->l2_warp_items * 32 + (int64_t)h.l2_warp_items * words;
                 } else {
@@ -1459,8 +1548,8 @@ int bf_sync(bf_ctx* c, bf_stats* st) {
                 snprintf(buf, sizeof buf, "work list: %llu items > capacity %llu; ", (unsigned long long)nwork, c->items_cap_used);
                 what += buf;
             }
-            // level1 = 1 cuts the queue into one segment per CTA: the fullest segment decides
-            const unsigned long long seg_need = c->level1 == 1 ? (unsigned long long)h.seg_max * (unsigned long long)c->num_sms : 0;
+            // the tensor-core level 1 cuts the queue into one segment per CTA: the fullest segment decides
+            const unsigned long long seg_need = c->level1 >= 1 ? (unsigned long long)h.seg_max * (unsigned long long)std::max(c->l1_segs, 1) : 0;
             if (h.n_units > c->queue_cap_used || seg_need > c->queue_cap_used) {
                 const unsigned long long need = std::max<unsigned long long>(h.n_units, seg_need);
                 c->units_capacity = (int64_t)(need + need / 4 + 1024 + c->num_sms);

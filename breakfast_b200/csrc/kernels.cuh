@@ -7,7 +7,7 @@
 //                                                               (replaces the np.isclose band, breakfast.py:250-254)
 //   K1b k_permute_store                                          staged sketches -> tile-blocked bitsets, fold planes,
 //                                                               +-1 int8 operands
-//   K2b k_schedule + k_exclusive_scan + k_expand_items           two-key band-pruned tile-pair work list
+//   K2b k_schedule (+ scan of the item counts by its last block) + k_expand_items   three-key band-pruned work list
 //   K3a k_pairs_l1_imma                                          level 1: int8 mma.sync on the 32-bit folds, survivors queued
 //   K3b k_pairs_l2_unit                                          level 2: exact 32-bit test, full-width XOR/POPC, candidates
 //                                                               (K3a+K3b replace sklearn _sparse_manhattan + _reduce_func,
@@ -50,6 +50,7 @@ struct DevCounters {
     unsigned int n_comp;
     unsigned int seg_max;              // fullest per-CTA segment of the level-2 pair queue (overflow check)
     unsigned int merge_fullest;        // longest compact label list of any rank in the exchange step (overflow check)
+    unsigned int sched_done;           // blocks of k_schedule that have finished (the last one scans the item counts)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -73,9 +74,14 @@ __device__ __forceinline__ sortkey_t sort_key(int64_t card, uint32_t s, uint32_t
 __device__ __forceinline__ uint32_t key_card(sortkey_t k) { return (uint32_t)(k >> 32); }
 
 // OR of all keys -> one atomic per warp; the radix passes run over the set bits of this word only
+// (a warp first looks at the word: once the early blocks have set the bits that occur, nobody sends an atomic any more -
+// tens of thousands of same-address atomics would otherwise queue up behind each other at about one per nanosecond)
 __device__ __forceinline__ void or_reduce_key(sortkey_t k, sortkey_t* __restrict__ or_key) {
     const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)k), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(k >> 32));
-    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(or_key, ((sortkey_t)hi << 32) | lo);
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) {
+        const sortkey_t mine = ((sortkey_t)hi << 32) | lo;
+        if (mine & ~__ldcg(or_key)) atomicOr(or_key, mine);
+    }
 }
 
 __global__ void k_card_keys(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows,
@@ -154,6 +160,7 @@ __device__ __forceinline__ uint32_t sort_digit(sortkey_t key, const uint32_t (&p
 // 36 us (round 1).  counts[block * 256 + digit].
 constexpr int SORT_THREADS = 1024;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_BATCH = 8;   // 32-row steps whose loads are in flight together
 
 __global__ void __launch_bounds__(SORT_THREADS, 1) k_radix_sort(SortBufs b, int64_t n, uint32_t* __restrict__ counts,
                                                                 const sortkey_t* __restrict__ or_key) {
@@ -187,13 +194,24 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) k_radix_sort(SortBufs b, int6
         }
         for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
         __syncthreads();
-        for (int64_t i0 = w0; i0 < w1; i0 += 32) {
-            const int64_t i = i0 + lane;
-            const bool valid = i < w1;
-            const uint32_t d = valid ? sort_digit(keys[i], pl.pos) : 256u + lane;  // invalid lanes match nobody
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[warp][d] += __popc(peers);
-            __syncwarp();
+        // SORT_BATCH steps of 32 rows at a time: their loads are issued together (one memory round trip per batch
+        // instead of one per step - a warp's part is a few hundred rows, so latency, not bandwidth, is what this costs)
+        for (int64_t i0 = w0; i0 < w1; i0 += 32 * SORT_BATCH) {
+            sortkey_t kb[SORT_BATCH];
+#pragma unroll
+            for (int u = 0; u < SORT_BATCH; ++u) {
+                const int64_t i = i0 + 32 * u + lane;
+                kb[u] = i < w1 ? __ldcg(&keys[i]) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < SORT_BATCH; ++u) {
+                if (i0 + 32 * u >= w1) break;   // warp-uniform
+                const bool valid = i0 + 32 * u + lane < w1;
+                const uint32_t d = valid ? sort_digit(kb[u], pl.pos) : 256u + lane;  // invalid lanes match nobody
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (valid && (peers & ((1u << lane) - 1u)) == 0) whist[warp][d] += __popc(peers);
+                __syncwarp();
+            }
         }
         __syncthreads();
         if (threadIdx.x < 256) {   // digit = threadIdx.x: exclusive prefix over the warps, the block's count to global memory
@@ -241,21 +259,31 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) k_radix_sort(SortBufs b, int6
         }
         __syncthreads();
         uint32_t* wpos = whist[warp];
-        for (int64_t i0 = w0; i0 < w1; i0 += 32) {
-            const int64_t i = i0 + lane;
-            const bool valid = i < w1;
-            const sortkey_t k = valid ? keys[i] : 0ull;
-            const uint32_t d = valid ? sort_digit(k, pl.pos) : 256u + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const unsigned below = peers & ((1u << lane) - 1u);
-            uint32_t pos = 0;
-            if (valid) pos = wpos[d] + __popc(below);
-            __syncwarp();
-            if (valid && below == 0) wpos[d] += __popc(peers);
-            __syncwarp();
-            if (valid) {
-                keys_out[pos] = k;
-                vals_out[pos] = vals[i];
+        for (int64_t i0 = w0; i0 < w1; i0 += 32 * SORT_BATCH) {
+            sortkey_t kb[SORT_BATCH];
+            int32_t vb[SORT_BATCH];
+#pragma unroll
+            for (int u = 0; u < SORT_BATCH; ++u) {
+                const int64_t i = i0 + 32 * u + lane;
+                kb[u] = i < w1 ? __ldcg(&keys[i]) : 0ull;
+                vb[u] = i < w1 ? __ldcg(&vals[i]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < SORT_BATCH; ++u) {
+                if (i0 + 32 * u >= w1) break;   // warp-uniform
+                const bool valid = i0 + 32 * u + lane < w1;
+                const uint32_t d = valid ? sort_digit(kb[u], pl.pos) : 256u + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const unsigned below = peers & ((1u << lane) - 1u);
+                uint32_t pos = 0;
+                if (valid) pos = wpos[d] + __popc(below);
+                __syncwarp();
+                if (valid && below == 0) wpos[d] += __popc(peers);
+                __syncwarp();
+                if (valid) {
+                    keys_out[pos] = kb[u];
+                    vals_out[pos] = vb[u];
+                }
             }
         }
         __threadfence();
@@ -263,54 +291,47 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) k_radix_sort(SortBufs b, int6
     }
 }
 
-// Single-block exclusive scan (in place), 8 elements per thread per sweep; total -> *total_out (may be
-// null).  `skip_if_zero` (may be null): when *skip_if_zero >> skip_shift == 0 the scan is not needed.
-template <typename T>
-__global__ void __launch_bounds__(1024) k_exclusive_scan(T* __restrict__ data, int64_t n, T* total_out,
-                                                         const uint32_t* __restrict__ skip_if_zero, int skip_shift) {
-    if (skip_if_zero && (*skip_if_zero >> skip_shift) == 0) return;
-    constexpr int PER = 8;
-    __shared__ T warp_sums[32];
-    __shared__ T carry_s;
+// Exclusive scan (in place) of `data` by one block of THREADS threads inside another kernel (k_schedule's last block);
+// total -> *total_out.  `data` was written by other blocks before a __threadfence, so it is read around L1.
+template <int THREADS>
+__device__ __forceinline__ void block_exclusive_scan_u64(unsigned long long* data, int64_t n, unsigned long long* total_out) {
+    constexpr int PER = 8, WARPS = THREADS / 32;
+    __shared__ unsigned long long warp_sums[WARPS];
+    __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024 * PER) {
+    for (int64_t base = 0; base < n; base += THREADS * PER) {
         const int64_t i0 = base + (int64_t)threadIdx.x * PER;
-        T v[PER];
-        T local = 0;
+        unsigned long long v[PER], local = 0;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            v[k] = (i0 + k < n) ? data[i0 + k] : (T)0;
+            v[k] = (i0 + k < n) ? __ldcg(&data[i0 + k]) : 0ull;
             local += v[k];
         }
-        T x = local;
+        unsigned long long x = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            T y = __shfl_up_sync(0xffffffffu, x, o);
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
         }
         if (lane == 31) warp_sums[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            T t = warp_sums[lane];
+        unsigned long long before = 0, all = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                T y = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += y;
-            }
-            warp_sums[lane] = t;  // inclusive over warps
+        for (int w = 0; w < WARPS; ++w) {
+            const unsigned long long t = warp_sums[w];
+            before += w < warp ? t : 0ull;
+            all += t;
         }
-        __syncthreads();
-        const T carry = carry_s;
-        T run = carry + (warp ? warp_sums[warp - 1] : (T)0) + (x - local);
+        unsigned long long run = carry_s + before + (x - local);
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             if (i0 + k < n) data[i0 + k] = run;
             run += v[k];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        if (threadIdx.x == 0) carry_s += all;
         __syncthreads();
     }
     if (threadIdx.x == 0 && total_out) *total_out = carry_s;
@@ -349,7 +370,10 @@ k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __r
                            int64_t nB, int max_dist, int triangular, int group, int n_keys, int n_ranges,
                            const SchedRange* __restrict__ table3, int n_table3, int32_t* __restrict__ jlo,
                            int32_t* __restrict__ jend, unsigned long long* __restrict__ count,
-                           unsigned long long* __restrict__ n_tilepairs) {
+                           unsigned long long* __restrict__ n_tilepairs, unsigned int* __restrict__ done,
+                           unsigned long long* __restrict__ n_work) {
+    // count[I] = work items of row tile I; the block that finishes last turns count[0 .. tA] into the exclusive prefix
+    // (count[tA] = *n_work = all items) - the scan used to be a launch of its own
     __shared__ int32_t raw_first[SCHED_THREADS], raw_end[SCHED_THREADS];
     __shared__ unsigned char raw_have[SCHED_THREADS];   // 0 = empty, 1 = range, 2 = the clamped group (listed once per tile)
     const int64_t tA = (nA + TILE - 1) / TILE, tB = (nB + TILE - 1) / TILE;
@@ -434,7 +458,7 @@ k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __r
         }
     }
     __syncthreads();
-    if (!active || r0 != 0) return;
+    if (active && r0 == 0) {
     // second pass, entry 0's thread: clip every range against the end of the previous one
     int64_t prev_end = triangular ? I : 0;
     unsigned long long tp_sum = 0, items_sum = 0;
@@ -472,6 +496,18 @@ k_schedule(const sortkey_t* __restrict__ keysA, int64_t nA, const sortkey_t* __r
     }
     count[I] = items_sum;
     if (tp_sum) atomicAdd(n_tilepairs, tp_sum);
+    }
+    // last block done: exclusive scan of the counts
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) count[tA] = 0;
+    __syncthreads();
+    block_exclusive_scan_u64<SCHED_THREADS>(count, tA + 1, n_work);
 }
 
 // ordered in-band count: for every x in X, #{y in Y : ||x| - |y|| <= d}.  The metric's candidate pairs are defined
@@ -575,6 +611,20 @@ __device__ __forceinline__ uint4 expand_pm1(uint32_t bits16) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// the same for TWO rows at once: byte k = e_a[k] + 64 e_b[k] (e = +1 for a clear bit, -1 for a set bit), i.e. 65, 63,
+// -63 or -65 - still an int8.  The int8 dot product of a +-1 row with this packed row is d_a + 64 d_b with
+// d = 32 - 2 popc(f xor f'): one MMA accumulator carries the tests of two column rows (see k_pairs_l1_imma2).
+__device__ __forceinline__ uint4 expand_pm1_pair(uint32_t a16, uint32_t b16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t sa = (((a16 >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;  // bit i -> byte i
+        const uint32_t sb = (((b16 >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        w[q] = 0x41414141u ^ (sa * 0x7eu) ^ (sb * 0x80u);   // 0x41 = 65, ^0x7e -> 63, ^0x80 -> -63, both -> -65
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ uint32_t fold_hash(uint32_t col, int log2m) {
     return (col * 2654435761u) >> (32 - log2m);  // multiplicative hash -> [0, m)
 }
@@ -619,10 +669,12 @@ __global__ void __launch_bounds__(256) k_pack_sketch(const int64_t* __restrict__
 
 // Stores of one packed row (128/256-bit sketches) at slot `row` of sorted tile `tile`: the sketch itself, its
 // 32-bit fold in the two level-1/level-2 plane orders and, for the tensor-core level 1, the +-1 expanded fold.
+// Called by all 128 threads of a tile's block (thread = row): with `packed8b` the int8 column operand holds TWO rows
+// per 32 bytes (rows 2p and 2p + 1, expand_pm1_pair; the odd row's fold comes from the neighbouring lane).
 template <int WORDS>
 __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64_t tile, int row, uint32_t* __restrict__ bits,
                                                uint32_t* __restrict__ foldA, uint32_t* __restrict__ foldB,
-                                               uint32_t* __restrict__ fold8a, uint4* __restrict__ fold8b) {
+                                               uint32_t* __restrict__ fold8a, uint4* __restrict__ fold8b, bool packed8b) {
     constexpr int K4 = WORDS / 4;
     uint4* dst = reinterpret_cast<uint4*>(bits) + (size_t)tile * (K4 * TILE);
 #pragma unroll
@@ -644,9 +696,18 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
         //  row operand: m16n8k32 A-fragment order - the 16 bytes {row r: k lo, row r+8: k lo, row r: k hi,
         //  row r+8: k hi} of lane (r%8)*4 + s4 of m-tile r/16 are contiguous, so a fragment is one LDS.128
         const uint4 e0 = expand_pm1(f & 0xffffu), e1 = expand_pm1(f >> 16);
-        uint4* tb = fold8b + (size_t)tile * (TILE * 2);
-        tb[row * 2 + 0] = e0;
-        tb[row * 2 + 1] = e1;
+        const uint32_t f_next = __shfl_down_sync(0xffffffffu, f, 1);   // fold of row + 1 (rows 2p, 2p + 1 share a warp)
+        if (packed8b) {
+            if ((row & 1) == 0) {
+                uint4* tb = fold8b + (size_t)tile * TILE + (row >> 1) * 2;   // 64 packed rows x 32 bytes per tile
+                tb[0] = expand_pm1_pair(f & 0xffffu, f_next & 0xffffu);
+                tb[1] = expand_pm1_pair(f >> 16, f_next >> 16);
+            }
+        } else {
+            uint4* tb = fold8b + (size_t)tile * (TILE * 2);
+            tb[row * 2 + 0] = e0;
+            tb[row * 2 + 1] = e1;
+        }
         uint32_t* ta = fold8a + (size_t)tile * (TILE * 8);
         const int m = row >> 4, h = (row >> 3) & 1, fr = row & 7;
         const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};   // bytes 4q .. 4q+3
@@ -871,8 +932,9 @@ __global__ void __launch_bounds__(TILE) k_permute_store(const uint32_t* __restri
                                                         const int32_t* __restrict__ perm, int64_t n,
                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ foldA,
                                                         uint32_t* __restrict__ foldB, uint32_t* __restrict__ fold8a,
-                                                        uint4* __restrict__ fold8b) {
+                                                        uint4* __restrict__ fold8b, int packed8b, int* __restrict__ parent_init) {
     const int64_t p = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    if (parent_init && p < n) parent_init[p] = (int)p;   // the union-find starts here too (one launch less per pass)
     uint32_t w[WORDS];
 #pragma unroll
     for (int t = 0; t < WORDS; ++t) w[t] = 0u;   // rows past n stay all-zero (never emitted: index check in the pair kernels)
@@ -884,7 +946,7 @@ __global__ void __launch_bounds__(TILE) k_permute_store(const uint32_t* __restri
             w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
         }
     }
-    pack_store_row<WORDS>(w, blockIdx.x, threadIdx.x, bits, foldA, foldB, fold8a, fold8b);
+    pack_store_row<WORDS>(w, blockIdx.x, threadIdx.x, bits, foldA, foldB, fold8a, fold8b, packed8b != 0);
 }
 
 // FULL: bit matrix pre-zeroed by the host (cudaMemsetAsync); one warp per row sets its bits.
@@ -1426,11 +1488,192 @@ k_pairs_l1_imma(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ f
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K3a-2: the same level 1 with TWO column rows per accumulator (default).  The column operand holds rows 2p and 2p + 1
+// of a tile as one int8 row e(2p) + 64 e(2p+1) (expand_pm1_pair: 65, 63, -63, -65), so one m16n8k32 MMA against the
+// +-1 row operand gives acc = d1 + 64 d2 with d = 32 - 2 popc(fa xor fb) of the two pairs - half the MMAs, half the
+// accumulators and half the operand bytes per evaluated pair.  Both tests come out of ONE multiply and a packed max:
+// with x = acc + 63 and w = x * 66560 = (x << 16) + (x << 10) (one IMAD: acc * 66560 + 63 * 66560),
+//     high half of w = x + floor(x / 64), strictly increasing in acc, and d2 >= thr  <=>  acc >= 64 thr - 32 (|d1| <= 32),
+//     low half of w  = ((d1 + 63) mod 64) << 10, as a signed 16-bit number 1024 (d1 - 1) for every even d1 in [-30, 32]
+//                      (d1 = -32, the complement fold, aliases d1 = 32: a false positive that level 2 rejects),
+// so a 3-input signed 16x2 max tree (VIMNMX3.S16x2, half an ALU op per accumulator; the multiply is an IMAD on the FMA
+// pipe) over a thread's accumulators decides both column rows at once: survivor  <=>  high >= 65 thr + 31 or
+// low >= 1024 (thr - 1), thr = 32 - 2 max_dist (max_dist >= 32: every pair survives, as it must).
+//   warp w: m-tiles 4 (w / 8) .. + 3 (64 rows) against the packed rows 8 (w % 8) .. + 7 (16 column rows) of every
+//   column tile: 4 A fragments in registers per item, per column tile one LDS.64 + 4 IMMAs + 16 IMADs + 8 packed maxes.
+//   A level-2 unit = the 8 x 4 pairs of one thread: rows (lane / 4) + 64 (w / 8) + 8 s, s < 8, columns
+//   16 (w % 8) + 4 (lane % 4) + {0, 1, 2, 3}.
+// ------------------------------------------------------------------------------------------
+constexpr int IMMA2_TILEB_BYTES = (TILE / 2) * 32;
+constexpr int IMMA2_STAGE_BYTES = IMMA_TILE_BYTES + IMMA_GROUP * IMMA2_TILEB_BYTES;
+template <int MINB> struct Imma2Cfg {
+    static constexpr int kStages = MINB == 1 ? 8 : 5;   // 160 KB for one CTA per SM, 2 x 100 KB for two
+    static constexpr int kSmemBytes = kStages * IMMA2_STAGE_BYTES + kStages * (8 + 8 + 8);
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(PAIR_THREADS, MINB)
+k_pairs_l1_imma2(const uint32_t* __restrict__ fold8A, const uint4* __restrict__ fold8P, int64_t nA, int64_t nB,
+                 const int2* __restrict__ items, unsigned long long items_cap,
+                 const unsigned long long* __restrict__ n_work, int max_dist, int triangular, int rank, int world,
+                 int pack_mul, int pack_add, int2* __restrict__ queue, unsigned long long queue_cap, unsigned* __restrict__ seg_counts,
+                 DevCounters* __restrict__ counters) {
+    // pack_mul = 66560 and pack_add = 63 * 66560 are passed as arguments so that acc * pack_mul + pack_add stays ONE
+    // IMAD (FMA pipe) instead of shifts and adds on the ALU pipe
+    constexpr int STAGES = Imma2Cfg<MINB>::kStages;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * IMMA2_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    int2* meta = reinterpret_cast<int2*>(empty_bar + STAGES);
+    __shared__ unsigned seg_cursor;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned seg_cap = (unsigned)min(queue_cap / gridDim.x, 0xffffffffull);   // one queue segment per CTA
+    int2* seg = queue + (size_t)blockIdx.x * seg_cap;
+    if (threadIdx.x == 0) {
+        seg_cursor = 0;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned long long W = min(*n_work, items_cap);
+    const unsigned long long first = (unsigned long long)rank + (unsigned long long)world * blockIdx.x;
+    const unsigned long long stride = (unsigned long long)world * gridDim.x;
+
+    if (warp == PAIR_CONSUMER_WARPS) {
+        uint32_t it = 0;
+        unsigned long long tp = 0;
+        for (unsigned long long k0 = 0;; k0 += 32) {
+            if (first + k0 * stride >= W) break;
+            const unsigned long long w = first + (k0 + lane) * stride;
+            int2 mine = make_int2(0, 0);
+            if (w < W) mine = __ldg(&items[w]);
+            for (int l = 0; l < 32; ++l) {
+                if (first + (k0 + l) * stride >= W) break;
+                const int Il = __shfl_sync(0xffffffffu, mine.x, l), Jp = __shfl_sync(0xffffffffu, mine.y, l);
+                if (lane == 0) {
+                    const int J0 = Jp & 0x1fffffff, cnt = ((unsigned)Jp >> 29) + 1;
+                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    meta[stage] = make_int2(Il, Jp);
+                    unsigned char* sa = smem + stage * IMMA2_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)IMMA_TILE_BYTES + (uint32_t)cnt * IMMA2_TILEB_BYTES);
+                    bulk_g2s(sa, fold8A + (size_t)Il * (TILE * 8), IMMA_TILE_BYTES, &full_bar[stage]);
+                    bulk_g2s(sa + IMMA_TILE_BYTES, fold8P + (size_t)J0 * TILE, (uint32_t)cnt * IMMA2_TILEB_BYTES, &full_bar[stage]);
+                    ++it;
+                    tp += cnt;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0 && tp) atomicAdd(&counters->tilepairs_rank, tp);
+        return;
+    }
+
+    const int thr = 32 - 2 * max_dist;
+    // packed thresholds (high half: the odd column row, low half: the even one); max_dist >= 32 passes everything
+    const int hi_thr = max_dist >= 32 ? -32768 : 65 * thr + 31, lo_thr = max_dist >= 32 ? -32768 : 1024 * (thr - 1);
+    const bool all_pass = max_dist >= 32;
+    const uint32_t thr_m1 = ((uint32_t)(hi_thr - 1) << 16) | ((uint32_t)(lo_thr - 1) & 0xffffu);   // (unused when all_pass)
+    constexpr uint32_t kNone = 0x80008000u;   // below any threshold in both halves
+    const int mhalf = warp >> 3, ngrp = warp & 7;
+    const int frow = lane >> 2, fk = (lane & 3) * 8;   // B fragment: packed row inside the warp's 8, byte offset of this lane's k slice
+    uint32_t stage = 0, ph = 0;
+    const uint32_t W32 = (uint32_t)W, stride32 = (uint32_t)stride;   // the work list holds at most 2^24 items
+    for (uint32_t w = (uint32_t)first; w < W32; w += stride32) {
+        mbar_wait(&full_bar[stage], ph);
+        const unsigned char* sA = smem + stage * IMMA2_STAGE_BYTES;
+        const unsigned char* sB = sA + IMMA_TILE_BYTES + (8 * ngrp + frow) * 32 + fk;
+        const int2 ij = meta[stage];
+        const int cnt = ((unsigned)ij.y >> 29) + 1;
+        uint4 a[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) a[m] = reinterpret_cast<const uint4*>(sA)[(4 * mhalf + m) * 32 + lane];
+        uint32_t mxj[IMMA_GROUP];
+#pragma unroll
+        for (int jt = 0; jt < IMMA_GROUP; ++jt) {
+            mxj[jt] = kNone;
+            if (jt >= cnt) continue;   // a partly filled item does not pay for its missing tiles
+            const uint2 b = *reinterpret_cast<const uint2*>(sB + jt * IMMA2_TILEB_BYTES);
+            int c[4][4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) imma_16832(c[m], a[m], b.x, b.y);
+            uint32_t p[16];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) p[4 * m + q] = (uint32_t)(c[m][q] * pack_mul + pack_add);   // one IMAD
+            uint32_t m0 = __vimax3_s16x2(p[0], p[1], p[2]), m1 = __vimax3_s16x2(p[3], p[4], p[5]);
+            m0 = __vimax3_s16x2(m0, p[6], p[7]);
+            m1 = __vimax3_s16x2(m1, p[8], p[9]);
+            m0 = __vimax3_s16x2(m0, p[10], p[11]);
+            m1 = __vimax3_s16x2(m1, p[12], p[13]);
+            m0 = __vimax3_s16x2(m0, p[14], p[15]);
+            mxj[jt] = __vmaxs2(m0, m1);
+        }
+        // One of this thread's 8 x 4 pairs of tile pair (I, J0 + jt) may be within max_dist -> the unit goes to this CTA's
+        // segment of the level-2 queue.  Rare per thread (2.6 % of the units at 10^6 profiles), but two warp-items in three
+        // have one: the test for the whole item is one more max tree + a packed compare ("some half above its threshold"
+        // <=> the packed max with thresholds - 1 is not thresholds - 1), and the warp appends its units with ONE update of
+        // the shared-memory cursor (prefix sum over the lanes' counts).
+        static_assert(IMMA_GROUP == 8, "the item test below is written for eight column tiles");
+        uint32_t any = __vimax3_s16x2(mxj[0], mxj[1], mxj[2]);
+        any = __vimax3_s16x2(any, mxj[3], mxj[4]);
+        any = __vimax3_s16x2(any, mxj[5], mxj[6]);
+        any = __vmaxs2(any, mxj[7]);
+        const bool mine = all_pass || __vmaxs2(any, thr_m1) != thr_m1;
+        if (__any_sync(0xffffffffu, mine)) {
+            uint32_t mask = 0;
+            if (mine) {
+#pragma unroll
+                for (int jt = 0; jt < IMMA_GROUP; ++jt)
+                    mask |= (jt < cnt && (all_pass || __vmaxs2(mxj[jt], thr_m1) != thr_m1) ? 1u : 0u) << jt;
+            }
+            const int n_mine = __popc(mask);
+            int incl = n_mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            unsigned base = 0;
+            if (lane == 31) base = atomicAdd(&seg_cursor, (unsigned)incl);
+            unsigned pos = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - n_mine);
+            while (mask) {
+                const int jt = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                if (pos < seg_cap) seg[pos] = make_int2(ij.x | (warp << 24), ((ij.y & 0x1fffffff) + jt) | (lane << 24));
+                ++pos;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) {
+            stage = 0;
+            ph ^= 1u;
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(PAIR_CONSUMER_WARPS * 32) : "memory");   // consumer warps only
+    if (threadIdx.x == 0) {
+        const unsigned n = seg_cursor;
+        seg_counts[blockIdx.x] = n;
+        if (n) {
+            atomicAdd(&counters->n_units, (unsigned long long)n);
+            atomicMax(&counters->seg_max, n);
+        }
+    }
+}
+
 // level 2 of the tensor-core level 1: one THREAD per queued unit = the 16 x 2 pairs (rows (tx/4) + 8 s of tile I,
 // columns 8 ty + 2 (tx%4) + {0, 1} of tile J) held by one accumulator-fragment lane.  The unit's 16 + 2 32-bit
 // folds are three contiguous loads (unit-order planes written by the pack kernel); only the pairs that pass the
 // exact 32-bit test (about one in sixty) fetch the two full sketches.
-template <int K4>
+// PACKED (units of k_pairs_l1_imma2): rows (tx/4) + 64 (ty/8) + 8 s, s < 8, columns 16 (ty%8) + 4 (tx%4) + {0..3} - the
+// unit's 8 + 4 folds are again three contiguous loads of the same planes.
+template <int K4, bool PACKED>
 __global__ void __launch_bounds__(256)
 k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, const uint4* __restrict__ foldA,
                 const uint2* __restrict__ foldB, int64_t nA, int64_t nB, const int2* __restrict__ queue,
@@ -1454,27 +1697,37 @@ k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB
       if (u < n) {
         const int2 unit = __ldg(&seg[u]);
         const int I = unit.x & 0x00ffffff, ty = (unit.x >> 24) & 15, J = unit.y & 0x00ffffff, tx = (unit.y >> 24) & 31;
-        const int r0 = tx >> 2, c0 = 8 * ty + 2 * (tx & 3);
-        const uint2 fb = __ldg(&foldB[((size_t)J * TILE + c0) >> 1]);
-        const uint4* fa4 = foldA + ((size_t)I * TILE + r0 * 16) / 4;
+        // NC columns per unit: bit NC s + j of `hits` = pair (row r0 + 8 s, column c0 + j) passes the 32-bit test
+        constexpr int NC = PACKED ? 4 : 2;
+        const int r0 = PACKED ? (tx >> 2) + 64 * (ty >> 3) : tx >> 2;
+        const int c0 = PACKED ? 16 * (ty & 7) + 4 * (tx & 3) : 8 * ty + 2 * (tx & 3);
+        uint32_t fb[NC];
+        if constexpr (PACKED) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(foldB) + (((size_t)J * TILE + c0) >> 2));
+            fb[0] = v.x; fb[1] = v.y; fb[2] = v.z; fb[3] = v.w;
+        } else {
+            const uint2 v = __ldg(&foldB[((size_t)J * TILE + c0) >> 1]);
+            fb[0] = v.x; fb[1] = v.y;
+        }
+        // unit-order plane: rows (r % 8) + 8 s of a tile are contiguous over s (imma_unit_pos)
+        const uint4* fa4 = foldA + ((size_t)I * TILE + imma_unit_pos(r0)) / 4;
         const int64_t gi0 = (int64_t)I * TILE + r0, gj0 = (int64_t)J * TILE + c0;
-        // pass 1, no loads beyond the folds: bit 2 s + j = pair (row r0 + 8 s, column c0 + j) passes the 32-bit test
+        // pass 1, no loads beyond the folds
         uint32_t hits = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 32 / NC / 4; ++q) {
             const uint4 fa = __ldg(&fa4[q]);
             const uint32_t f[4] = {fa.x, fa.y, fa.z, fa.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                hits |= (__popc(f[t] ^ fb.x) <= threshold ? 1u : 0u) << (2 * (4 * q + t));
-                hits |= (__popc(f[t] ^ fb.y) <= threshold ? 2u : 0u) << (2 * (4 * q + t));
-            }
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) hits |= (__popc(f[t] ^ fb[j]) <= threshold ? 1u : 0u) << (NC * (4 * q + t) + j);
         }
         // pass 2: the lanes of a warp walk their own survivors together (one or two rounds, whatever the slots)
         while (hits) {
             const int bit = __ffs(hits) - 1;
             hits &= hits - 1;
-            const int s = bit >> 1, j = bit & 1;
+            const int s = bit / NC, j = bit % NC;
             const int64_t gi = gi0 + 8 * s, gj = gj0 + j;
             if (gi >= nA || gj >= nB || (triangular && gi >= gj)) continue;
             ++full_checks;
@@ -1606,8 +1859,14 @@ __global__ void __launch_bounds__(256) k_uf_labels(int* __restrict__ parent, int
         labels[i] = r;
         is_root = r == (int)i;
     }
+    // one atomic per block: a same-address atomic per warp (31 250 of them at 10^6 rows) was most of this kernel's time
+    __shared__ unsigned int block_roots;
+    if (threadIdx.x == 0) block_roots = 0;
+    __syncthreads();
     const unsigned int m = __ballot_sync(0xffffffffu, is_root);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_roots, (unsigned int)__popc(m));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&block_roots, (unsigned int)__popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0 && block_roots) atomicAdd(n_roots, block_roots);
 }
 
 __global__ void k_uf_edges(int* __restrict__ parent, const int32_t* __restrict__ src,
@@ -1712,11 +1971,30 @@ __device__ __forceinline__ void row_extent(const RowStore& m, int r, int64_t& ba
     base = __ldg(&m.indptr[r]);
     len = (int)(__ldg(&m.indptr[r + 1]) - base);   // a row has fewer than 2^31 columns
 }
+// The compact resident form (CSR16, see k_csr16_encode): half the bytes per column.  A row's position is handed around
+// as base | split << 40 (offsets are below 2^32, split = how many of the row's ascending columns are below 65536, at most
+// 65535), so that row_col can rebuild the 17-bit column without another lookup.
+struct RowStore16 {
+    const uint32_t* indptr32;
+    const uint16_t* split;   // null: every column is below 65536
+    const uint16_t* lo;
+};
+__device__ __forceinline__ int row_col(const RowStore16& m, int64_t base, int k) {
+    const uint32_t b = (uint32_t)base;
+    const int sp = (int)(base >> 40);
+    return (int)__ldg(m.lo + b + k) | (k >= sp ? 0x10000 : 0);
+}
+__device__ __forceinline__ void row_extent(const RowStore16& m, int r, int64_t& base, int& len) {
+    const uint32_t b = __ldg(&m.indptr32[r]);
+    len = (int)(__ldg(&m.indptr32[r + 1]) - b);
+    const int64_t sp = m.split ? (int64_t)__ldg(&m.split[r]) : (int64_t)0xffffff;
+    base = (int64_t)b | (sp << 40);
+}
 
 // One chunk of 128 columns of the shorter row A and the longer row B of a candidate, lane t holding positions
 // base + t + 32 s (s < 4); lane t < NW also holds B[base - NW + t] and B[base + 128 + t] (the halo).
-template <int NW>
-__device__ __forceinline__ void verify_load_chunk(const RowStore& m, int lane, int base, int64_t ia, int la, int64_t ib, int lb,
+template <int NW, typename Rows>
+__device__ __forceinline__ void verify_load_chunk(const Rows& m, int lane, int base, int64_t ia, int la, int64_t ib, int lb,
                                                   int (&av)[4], int (&bv)[4], int& halo_lo, int& halo_hi) {
 #pragma unroll
     for (int sw = 0; sw < 4; ++sw) {
@@ -1776,7 +2054,8 @@ __device__ __forceinline__ int verify_match_chunk(int lane, const int (&av)[4], 
 
 // Generic form of the windowed match for one candidate, whole warp (any max_dist, rows of any length): every lane
 // strides over A and looks B up in the +-max_dist window.  Returns this lane's share of |A n B|.
-__device__ __forceinline__ int verify_pair_windowed(const RowStore& m, int lane, int64_t ia, int la, int64_t ib, int lb, int max_dist) {
+template <typename Rows>
+__device__ __forceinline__ int verify_pair_windowed(const Rows& m, int lane, int64_t ia, int la, int64_t ib, int lb, int max_dist) {
     int inter = 0;
     for (int k = lane; k < la; k += 32) {
         const int x = row_col(m, ia, k);
@@ -1806,10 +2085,10 @@ __device__ __forceinline__ void verify_emit(unsigned int edge_mask, int lane, in
     }
 }
 
-template <int DWIN>
+template <int DWIN, typename Rows>
 __global__ void __launch_bounds__(256)
 k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
-               const int32_t* __restrict__ permB, const RowStore m, int max_dist, int already_exact,
+               const int32_t* __restrict__ permB, const Rows m, int max_dist, int already_exact,
                const unsigned char* __restrict__ is_query, int* __restrict__ parent, uint2* __restrict__ edges,
                unsigned long long edge_cap, DevCounters* __restrict__ counters) {
     const unsigned long long n = min(counters->n_cand, cand_cap);
@@ -1868,7 +2147,7 @@ k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, cons
                     constexpr int NW = DWIN > 0 ? DWIN : 1;
                     int av[4], bv[4], halo_lo, halo_hi;
                     for (int cbase = 0; cbase < la; cbase += 128) {
-                        verify_load_chunk<NW>(m, lane, cbase, ia, la, ib, lb, av, bv, halo_lo, halo_hi);
+                        verify_load_chunk<NW, Rows>(m, lane, cbase, ia, la, ib, lb, av, bv, halo_lo, halo_hi);
                         inter += verify_match_chunk<NW>(lane, av, bv, halo_lo, halo_hi);
                     }
                 } else {

@@ -110,8 +110,9 @@ void bf_ctx_destroy(bf_ctx* ctx);
  * "want_edges" (0/1), "cand_capacity" (entries), "blocks_per_sm",
  * "two_level" (0/1, default 1: 32-bit first-level fold inside the pair kernel for
  * single-chunk sketches; exact either way), "level1" (0 = level 1 on the integer
- * pipes, 1 = on the tensor cores: int8 mma.sync on +-1 expanded folds; 128/256-bit
- * sketches), "items_capacity" / "units_capacity" (entries of the expanded work list and
+ * pipes, 1 = on the tensor cores: int8 mma.sync on +-1 expanded folds, 2 (default) = the same with two
+ * column rows per accumulator; 128/256-bit sketches), "l1_ctas" (CTAs per SM of the level-1 kernel of
+ * "level1" = 2: 1 or 2, 0 = default), "items_capacity" / "units_capacity" (entries of the expanded work list and
  * of the level-2 queue, 0 = automatic), "merge_capacity" (entries per rank of the compact label exchange of a
  * multi-GPU pass, 0 = automatic). */
 int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);

@@ -96,9 +96,10 @@ def test_cluster_and_edges_match_oracle(n, max_dist, engine):
 
 
 @pytest.mark.parametrize("max_dist", [1, 2, 3, 5])
-@pytest.mark.parametrize("level1", [0, 1])
+@pytest.mark.parametrize("level1", [0, 1, 2])
 def test_both_level1_kernels_are_exact(level1, max_dist):
-    """level 1 on the integer pipes (POPC / POPC-free hybrid) and on the tensor cores (int8 mma.sync)"""
+    """level 1 on the integer pipes (POPC / POPC-free hybrid) and on the tensor cores (int8 mma.sync; 2 = two column
+    rows per accumulator, the default)"""
     indptr, indices, n_cols = synth.generate(6000, seed=91).csr()
     want, ne = oracle.cluster(indptr, indices, max_dist)
     with _native.Context(level1=level1, sketch_bits=128) as ctx:
@@ -107,8 +108,8 @@ def test_both_level1_kernels_are_exact(level1, max_dist):
         assert np.array_equal(ctx.download_labels(), want) and st.n_edges == ne
 
 
-@pytest.mark.parametrize("max_dist", [8, 9, 16, 32])
-@pytest.mark.parametrize("level1", [0, 1])
+@pytest.mark.parametrize("max_dist", [8, 9, 15, 16, 31, 32, 40])
+@pytest.mark.parametrize("level1", [0, 1, 2])
 @pytest.mark.parametrize("bits", [128, 256])
 def test_large_max_dist_where_the_32_bit_level_cannot_reject(bits, level1, max_dist):
     """from max_dist 16 on the 32-bit level-1 test passes every pair (threshold 32 - 2 d <= 0) and the work falls to
@@ -120,6 +121,29 @@ def test_large_max_dist_where_the_32_bit_level_cannot_reject(bits, level1, max_d
         ctx.upload_csr(indptr, indices, n_cols)
         st = ctx.run_sync(max_dist)
         assert np.array_equal(ctx.download_labels(), want) and st.n_edges == ne
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("max_dist", [1, 2, 4])
+def test_packed_level1_matches_the_plain_tensor_core_level1(ctas, max_dist):
+    """k_pairs_l1_imma2 (two column rows per accumulator, one or two CTAs per SM) against k_pairs_l1_imma: same candidates
+    after level 2 (both levels are exact 32-bit fold tests, level 1 may only add the complement-fold alias), same edges,
+    same labels; rectangle run included (query rows = every third row)."""
+    indptr, indices, n_cols = synth.generate(20000, seed=5).csr()
+    q = np.arange(0, 20000, 3, dtype=np.int32)
+    res = []
+    for level1, opts in ((1, {}), (2, {"l1_ctas": ctas})):
+        with _native.Context(level1=level1, sketch_bits=128, want_edges=1, **opts) as ctx:
+            ctx.upload_csr(indptr, indices, n_cols)
+            st = ctx.run_sync(max_dist)
+            labels, edges = ctx.download_labels(), ctx.download_edges()
+            ctx.upload_csr(indptr, indices, n_cols, query_rows=q)
+            st_q = ctx.run_sync(max_dist)
+            res.append((labels, sorted(zip(*edges[:2])), st.n_candidates, st.n_edges, st_q.n_candidates, st_q.n_edges))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][1:] == res[1][1:]
+    want, ne = oracle.cluster(indptr, indices, max_dist)
+    assert np.array_equal(res[1][0], want) and res[1][3] == ne
 
 
 @pytest.mark.parametrize("bits", [128, 256, 512, 1024, 2048])
@@ -615,9 +639,10 @@ def _run_ctx(indptr, indices, n_cols, max_dist, query_rows=None, **options):
 @pytest.mark.parametrize("shape", ["cols<=65536", "cols>65536", "cols>131072", "long_rows", "ragged"])
 @pytest.mark.parametrize("max_dist", [1, 2, 3, 5])
 def test_resident_compact_form_changes_nothing(shape, max_dist):
-    """bf_upload_csr derives the compact resident form (k_csr16_encode) and the sketch pass + verification then read it
-    (k_pack_sketch_rows16, k_verify_unite<., true>): same labels and edges as with the plain CSR (option resident_csr16
-    = 0) and as the oracle - also where the matrix is not representable and the plain form has to stay in charge"""
+    """bf_upload_csr derives the compact resident form (k_csr16_encode) and the sketch pass (k_pack_sketch_rows16) and,
+    with option verify_csr16 = 1, the verification (k_verify_unite<., RowStore16>) then read it: same labels and edges
+    as with the plain CSR (option resident_csr16 = 0) and as the oracle - also where the matrix is not representable
+    and the plain form has to stay in charge"""
     rng = np.random.default_rng(7 + max_dist)
     if shape in ("cols<=65536", "cols>65536", "cols>131072"):
         ip, ix, nc = synth.generate(6000, seed=31).csr()
@@ -642,10 +667,10 @@ def test_resident_compact_form_changes_nothing(shape, max_dist):
         ip, ix, nc = rows_to_csr(rows, 130000)
     want_labels, _ = oracle.cluster(ip, ix, max_dist)
     ws, wd = oracle.edges(ip, ix, max_dist)
-    for resident in (1, 0):
-        labels, src, dst, st = _run_ctx(ip, ix, nc, max_dist, resident_csr16=resident)
-        assert np.array_equal(labels, want_labels), resident
-        assert np.array_equal(src, ws) and np.array_equal(dst, wd), resident
+    for resident, verify16 in ((1, 0), (1, 1), (0, 0)):
+        labels, src, dst, st = _run_ctx(ip, ix, nc, max_dist, resident_csr16=resident, verify_csr16=verify16)
+        assert np.array_equal(labels, want_labels), (resident, verify16)
+        assert np.array_equal(src, ws) and np.array_equal(dst, wd), (resident, verify16)
 
 
 def test_resident_compact_form_rectangle_and_unsorted_rows():

@@ -55,3 +55,34 @@ def test_schedule_mirror_loses_no_edge(max_dist, n_keys):
     assert all((int(i), int(j)) in covered for i, j in zip(a, b))
     if n_keys > 1:
         assert len(covered) <= schedule_sim.tile_pairs(indptr, indices, max_dist, n_keys - 1)
+
+
+def test_packed_pair_threshold_arithmetic_of_the_tensor_core_level1():
+    """CPU restatement of k_pairs_l1_imma2's survivor test (csrc/kernels.cuh): one accumulator holds
+    acc = d1 + 64 d2 (d = 32 - 2 popc of the two pairs); w = (acc + 63) * 66560 puts a monotone image of acc in the high
+    16 bits and ((d1 + 63) mod 64) << 10 in the low 16 bits; both halves are compared as signed 16-bit numbers.
+    The test must pass exactly the accumulators with d1 >= thr or d2 >= thr, plus the alias d1 = -32."""
+    pop = np.arange(0, 33)
+    d = 32 - 2 * pop
+    d1, d2 = np.meshgrid(d, d, indexing="ij")
+    acc = (d1 + 64 * d2).astype(np.int64)
+    w = ((acc + 63) * 66560).astype(np.int64)
+    assert np.abs(w).max() < 2 ** 31
+    hi = w >> 16                                    # arithmetic shift: floor
+    lo = ((w & 0xFFFF) ^ 0x8000) - 0x8000           # low half as a signed 16-bit number
+    assert hi.max() < 2 ** 15 and hi.min() >= -2 ** 15
+    for max_dist in range(0, 32):
+        thr = 32 - 2 * max_dist
+        hi_thr, lo_thr = 65 * thr + 31, 1024 * (thr - 1)
+        assert -2 ** 15 <= lo_thr < 2 ** 15
+        got = (hi >= hi_thr) | (lo >= lo_thr)
+        want = (d1 >= thr) | (d2 >= thr)
+        assert not (want & ~got).any(), f"max_dist {max_dist}: a survivor is lost"
+        extra = got & ~want
+        assert (d1[extra] == -32).all(), f"max_dist {max_dist}: false positives beyond the complement alias"
+    # the packed int8 operand: e1 + 64 e2 with e = +1 / -1 fits an int8 and the byte trick of expand_pm1_pair gives it
+    for a in (0, 1):
+        for b in (0, 1):
+            byte = 0x41 ^ (0x7E if a else 0) ^ (0x80 if b else 0)
+            val = byte - 256 if byte >= 128 else byte
+            assert val == (-1 if a else 1) + 64 * (-1 if b else 1)
