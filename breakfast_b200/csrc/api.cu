@@ -166,6 +166,7 @@ struct bf_ctx {
     int level1 = 2;             // 2 = tensor cores, two column rows per accumulator (k_pairs_l1_imma2, default),
                                 // 1 = tensor cores (k_pairs_l1_imma), 0 = integer pipes (k_pairs_l1)
     int l1_ctas = 0;            // CTAs per SM of k_pairs_l1_imma2 (1 or 2; 0 = the default, kL1CtasDefault)
+    int l2_sub = 0;             // option "l2_sub": CTAs of k_pairs_l2_unit per queue segment (0 = default)
     int l1_segs = 0;            // segments of the level-2 queue of the last pass (= the grid of the tensor-core level 1)
     int64_t items_capacity = 0;  // 0 = auto
     int64_t units_capacity = 0;  // 0 = auto (level-2 queue)
@@ -455,7 +456,7 @@ int exchange_labels(bf_ctx* c) {
     CKLC(c);
     NCK(nc.AllGather(mine, c->xchg.p, words_rank * sizeof(unsigned long long), bfnccl::kUint8, c->comm, c->stream));
     k_uf_merge_pairs<<<grid_for((int64_t)cap * c->world, 256), 256, 0, c->stream>>>(
-        c->parent.as<int>(), c->xchg.as<unsigned long long>(), c->world, cap, &c->counters.as<DevCounters>()->merge_fullest);
+        c->parent.as<int>(), c->xchg.as<unsigned long long>(), c->world, c->rank, cap, &c->counters.as<DevCounters>()->merge_fullest);
     CKLC(c);
     CK(cudaEventRecord(c->ev_aux[1], c->stream));
     c->ms_merge = -1.f;  // resolved in bf_sync
@@ -575,8 +576,11 @@ int launch_two_kernel_imma(bf_ctx* c, const uint4* A, const uint4* B, int64_t nA
     const uint2* fb = c->foldsB[1].as<uint2>();
     auto l2 = packed ? (c->K4 == 1 ? k_pairs_l2_unit<1, true> : k_pairs_l2_unit<2, true>)
                      : (c->K4 == 1 ? k_pairs_l2_unit<1, false> : k_pairs_l2_unit<2, false>);
-    l2<<<c->l1_segs * L2_SUB, 256, 0, c->stream>>>(A, B, fa, fb, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(),
-                                                  c->l1_segs, c->max_dist, tri, c->cand.as<uint2>(), c->cand_cap_used,
+    // CTAs of level 2 per queue segment (measured at 10^6 profiles with two level-1 CTAs per SM: 16 -> 42 us, 32 -> 44 us,
+    // 64 -> 50 us; a segment then holds about 6 000 units)
+    const int n_sub = c->l2_sub > 0 ? c->l2_sub : (packed ? std::max(1, L2_SUB / (2 * ctas)) : L2_SUB);
+    l2<<<c->l1_segs * n_sub, 256, 0, c->stream>>>(A, B, fa, fb, nA, nB, c->queue.as<int2>(), c->queue_cap_used, c->segcnt.as<unsigned>(),
+                                                  c->l1_segs, n_sub, c->max_dist, tri, c->cand.as<uint2>(), c->cand_cap_used,
                                                   c->counters.as<DevCounters>());
     CKLC(c);
     return BF_OK;
@@ -819,6 +823,9 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
     } else if (k == "level1") {
         if (value < 0 || value > 2) return fail(BF_ERR_INVALID, "level1 must be 0 (integer pipes), 1 (tensor cores) or 2 (tensor cores, two column rows per accumulator)");
         c->level1 = (int)value;
+    } else if (k == "l2_sub") {
+        if (value < 0 || value > 1024) return fail(BF_ERR_INVALID, "l2_sub must be in [0, 1024]");
+        c->l2_sub = (int)value;
     } else if (k == "l1_ctas") {
         if (value < 0 || value > 2) return fail(BF_ERR_INVALID, "l1_ctas must be 0 (default), 1 or 2");
         c->l1_ctas = (int)value;

@@ -708,6 +708,8 @@ __device__ __forceinline__ void pack_store_row(const uint32_t (&w)[WORDS], int64
             tb[row * 2 + 0] = e0;
             tb[row * 2 + 1] = e1;
         }
+        // (staging the tile in shared memory and writing it out with coalesced 16-byte stores was measured: no gain, 33.8 us
+        // either way at 10^6 rows - the scattered words of a tile merge in L2)
         uint32_t* ta = fold8a + (size_t)tile * (TILE * 8);
         const int m = row >> 4, h = (row >> 3) & 1, fr = row & 7;
         const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};   // bytes 4q .. 4q+3
@@ -1348,7 +1350,8 @@ k_pairs_l1(const uint32_t* __restrict__ foldA, const uint32_t* __restrict__ fold
 constexpr int IMMA_STAGES = 5;
 constexpr int IMMA_GROUP = 8;    // column tiles per work item of the tensor-core level 1 (runs are six tiles long on average)
 constexpr int L2_CBUF = 1024;   // candidates a CTA of k_pairs_l2_unit collects per round before one cursor update
-constexpr int L2_SUB = 64;      // CTAs of k_pairs_l2_unit per queue segment (one unit per thread for segments up to 16 K units)
+constexpr int L2_SUB = 64;      // CTAs of k_pairs_l2_unit per queue segment when level 1 ran one CTA per SM (one unit per thread
+                                // for segments up to 16 K units); halved when it ran two (half as many units per segment)
 constexpr int IMMA_TILE_BYTES = TILE * 32;
 constexpr int IMMA_STAGE_BYTES = (1 + IMMA_GROUP) * IMMA_TILE_BYTES;
 constexpr int IMMA_SMEM_BYTES = IMMA_STAGES * IMMA_STAGE_BYTES + IMMA_STAGES * (8 + 8 + 8);
@@ -1677,11 +1680,11 @@ template <int K4, bool PACKED>
 __global__ void __launch_bounds__(256)
 k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB, const uint4* __restrict__ foldA,
                 const uint2* __restrict__ foldB, int64_t nA, int64_t nB, const int2* __restrict__ queue,
-                unsigned long long queue_cap, const unsigned* __restrict__ seg_counts, int n_segs, int threshold,
+                unsigned long long queue_cap, const unsigned* __restrict__ seg_counts, int n_segs, int n_sub, int threshold,
                 int triangular, uint2* __restrict__ cand, unsigned long long cand_cap, DevCounters* __restrict__ counters) {
-    // blockIdx.x = segment * L2_SUB + slice: the CTAs of one segment stride over its units
+    // blockIdx.x = segment * n_sub + slice: the CTAs of one segment stride over its units
     const unsigned seg_cap = (unsigned)min(queue_cap / (unsigned)n_segs, 0xffffffffull);
-    const int sgm = blockIdx.x / L2_SUB, sub = blockIdx.x % L2_SUB;
+    const int sgm = blockIdx.x / n_sub, sub = blockIdx.x % n_sub;
     const unsigned n = min(__ldg(&seg_counts[sgm]), seg_cap);
     const int2* seg = queue + (size_t)sgm * seg_cap;
     // candidates are collected per CTA and appended with ONE global cursor update per round: a contended
@@ -1692,7 +1695,7 @@ k_pairs_l2_unit(const uint4* __restrict__ bitsA, const uint4* __restrict__ bitsB
     if (threadIdx.x == 0) cbuf_n = checks_n = 0;
     __syncthreads();
     unsigned full_checks = 0;
-    for (unsigned u0 = sub * blockDim.x; u0 < n; u0 += L2_SUB * blockDim.x) {   // uniform over the CTA
+    for (unsigned u0 = sub * blockDim.x; u0 < n; u0 += n_sub * blockDim.x) {   // uniform over the CTA
       const unsigned u = u0 + threadIdx.x;
       if (u < n) {
         const int2 unit = __ldg(&seg[u]);
@@ -1909,22 +1912,34 @@ __global__ void __launch_bounds__(256) k_uf_compact(int* __restrict__ parent, in
         r = uf_find(parent, (int)i);
         changed = r != (int)i;
     }
+    // one cursor update per block (a same-address atomic per warp is 31 250 atomics at 10^6 rows)
+    __shared__ unsigned int warp_n[8];
+    __shared__ unsigned long long block_base;
     const unsigned int m = __ballot_sync(0xffffffffu, changed);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&mine[0], (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (changed) {
-            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < cap) mine[1 + pos] = (unsigned long long)(uint32_t)i | ((unsigned long long)(uint32_t)r << 32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_n[warp] = (unsigned int)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned int c = warp_n[w];
+            warp_n[w] = total;   // exclusive prefix over the warps
+            total += c;
         }
+        block_base = total ? atomicAdd(&mine[0], (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    if (changed) {
+        const unsigned long long pos = block_base + warp_n[warp] + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) mine[1 + pos] = (unsigned long long)(uint32_t)i | ((unsigned long long)(uint32_t)r << 32);
     }
 }
 
 // gathered[r] = the compact list of rank r ((cap + 1) words each): union(row, root) for every entry of every rank
+// (this rank's own list is already in its forest: only its length is looked at)
 __global__ void __launch_bounds__(256) k_uf_merge_pairs(int* __restrict__ parent, const unsigned long long* __restrict__ gathered,
-                                                        int world, unsigned long long cap, unsigned int* __restrict__ fullest) {
+                                                        int world, int rank, unsigned long long cap, unsigned int* __restrict__ fullest) {
     const unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const int r = (int)(idx / cap);
     if (r >= world) return;
@@ -1932,7 +1947,7 @@ __global__ void __launch_bounds__(256) k_uf_merge_pairs(int* __restrict__ parent
     const unsigned long long* lst = gathered + (size_t)r * (cap + 1);
     const unsigned long long cnt = lst[0];
     if (j == 0) atomicMax(fullest, (unsigned int)min(cnt, 0xffffffffull));
-    if (j < min(cnt, cap)) {
+    if (r != rank && j < min(cnt, cap)) {
         const unsigned long long e = lst[1 + j];
         uf_unite(parent, (int)(uint32_t)e, (int)(uint32_t)(e >> 32));
     }
@@ -2085,6 +2100,9 @@ __device__ __forceinline__ void verify_emit(unsigned int edge_mask, int lane, in
     }
 }
 
+// (Measured at 10^6 profiles, max-dist 1, 750 k candidates: 170 us with 44 registers / 5 resident blocks per SM; a
+// register budget for 6 or 8 blocks - 40 / 32 registers, a few spills - 180 / 183 us, so more warps in flight do not
+// help: the kernel moves 541 MB of scattered 360-byte rows at 3.2 TB/s, which is what random sector-granular reads reach.)
 template <int DWIN, typename Rows>
 __global__ void __launch_bounds__(256)
 k_verify_unite(const uint2* __restrict__ cand, unsigned long long cand_cap, const int32_t* __restrict__ permA,
