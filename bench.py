@@ -557,6 +557,25 @@ def main():
             "cpu_baseline": cpu,
             "phases_ms": {k: getattr(st, k) for k in ("ms_sort", "ms_pack", "ms_pairs", "ms_verify", "ms_cc", "ms_merge")},
         }
+        # second kernel of the step: the exact verification, an HBM-bound gather of two CSR rows per candidate
+        # (algorithmic bytes: the two rows + their extents; peak: MEASURED_PEAKS.json, else the profiling guide's fallback)
+        if args.engine == "sketch" and world == 1 and st.n_candidates > 0:
+            peaks_file = ROOT / "MEASURED_PEAKS.json"
+            hbm = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+            row_bytes = 4.0 * indices.size / n + 16.0
+            vbytes = st.n_candidates * 2 * row_bytes
+            vtraffic = None
+            try:
+                vtraffic = json.loads(tf.read_text()).get(f"k_verify_unite_{args.engine}_{st.bits_per_row}_n{n}")
+            except Exception:
+                pass
+            line["roofline_verify"] = {"kernel": "k_verify_unite<max_dist> (exact |A xor B| on the CSR rows of the sketch survivors + union-find hook)",
+                                       "bound": "hbm", "achieved": vbytes / (st.ms_verify * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                       "frac": vbytes / (st.ms_verify * 1e-3) / 1e9 / hbm, "traffic": vtraffic,
+                                       "ms_per_launch": st.ms_verify, "candidates": st.n_candidates,
+                                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks_file.exists() else "fallback 6650 GB/s",
+                                       "note": "scattered 360-byte rows: 12-13 sectors per row at random addresses; more resident warps or "
+                                               "half the bytes (compact form) were measured slower (DESIGN.md section 3)"}
         line.update(extras)
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -22,9 +22,9 @@ for w in $what; do
         --log-file gpurun_out/launches.csv $BENCH_SHORT > gpurun_out/ncu_launches.log 2>&1
       echo "launch list rc=$?" ;;
     ncu)
-      # the three biggest kernels of a step, one launch each, after the warm-up steps (3 kernels x 4 passes skipped)
-      ncu --set full --clock-control none --import-source on -k 'regex:k_pairs_l1_imma|k_verify_unite|k_pack_sketch_rows16' \
-        --launch-skip 12 --launch-count 3 -f -o gpurun_out/top3 $BENCH_SHORT > gpurun_out/ncu_top3.log 2>&1
+      # the five biggest kernels of a step, one launch each, after the warm-up steps (5 kernels x 4 passes skipped)
+      ncu --set full --clock-control none --import-source on -k 'regex:k_pairs_l1_imma2|k_verify_unite|k_pack_sketch_rows16|k_radix_sort|k_pairs_l2_unit' \
+        --launch-skip 20 --launch-count 5 -f -o gpurun_out/top5 $BENCH_SHORT > gpurun_out/ncu_top5.log 2>&1
       echo "ncu rc=$?" ;;
   esac
 done
