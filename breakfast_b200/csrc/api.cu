@@ -208,6 +208,7 @@ struct bf_ctx {
     int pack16_variant = 1;   // one lane per row, ATOMS (fastest of the four, profiles/)
     int active_slot = -1;  // slot the current matrix lives in, -1 = caller-owned memory (bf_adopt_csr_device) or none
     bool use16 = false;    // this pass's sketch kernel reads the compact form
+    int shard_pack_from = 16;   // option "shard_pack_from"
     int verify16 = 0;      // option "verify_csr16" = 1: the exact verification reads its rows from the compact form too
                            // (measured: 217 us against 170 us on the plain CSR at 10^6 profiles - half the bytes, but 16-bit
                            // loads and the rebuilt 17th bit cost more than the bytes save; kept as an option)
@@ -363,9 +364,11 @@ int encode_c16(bf_ctx* c, int slot, int64_t n_rows, int64_t nnz, cudaStream_t st
 // rows the staging arrays must hold: with a communicator every rank owns an equal, block-aligned share (the last ones
 // possibly past the end), so that the shares can be all-gathered in place
 inline bool dist_run(const bf_ctx* c) { return c->comm != nullptr && c->world > 1; }
-// The sketch + key pass is sharded over the ranks only from 8 ranks on: the all-gather of the shares costs about 0.08 ms
-// on NVLink whatever the rank count (measured, profiles/r02_scale_*), the pass itself 0.115 ms / world
-inline bool shard_pack(const bf_ctx* c) { return dist_run(c) && c->world >= 8; }
+// Sharding the sketch + key pass over the ranks costs an all-gather of 24 bytes per row (about 0.08 ms on NVLink whatever
+// the rank count), the pass itself 0.074 ms / world since it streams the compact form: measured on 8 B200s the sketch +
+// sort phase takes 0.243 ms sharded against 0.20 ms replicated (profiles/r02_bench_n{2,8}_final.json), so the pass is
+// replicated on one box; option "shard_pack_from" = the rank count from which it is sharded (default 16: never on 8 GPUs)
+inline bool shard_pack(const bf_ctx* c) { return dist_run(c) && c->world >= c->shard_pack_from; }
 inline int64_t staged_rows(const bf_ctx* c) {
     const int64_t blocks = ceil_div(c->n_rows, TILE);
     return shard_pack(c) ? ceil_div(blocks, c->world) * c->world * TILE : blocks * TILE;
@@ -840,6 +843,9 @@ int bf_ctx_set_option(bf_ctx* c, const char* key, int64_t value) {
         c->pack16_variant = (int)value;
     } else if (k == "resident_csr16") {
         c->resident16 = value ? 1 : 0;   // 0: the sketch pass streams the plain CSR
+    } else if (k == "shard_pack_from") {
+        if (value < 2) return fail(BF_ERR_INVALID, "shard_pack_from must be >= 2");
+        c->shard_pack_from = (int)value;
     } else if (k == "verify_csr16") {
         c->verify16 = value ? 1 : 0;
     } else if (k == "blocks_per_sm") {

@@ -37,6 +37,8 @@ def _context_options() -> dict:
         opts["sketch_bits"] = int(os.environ["BREAKFAST_B200_SKETCH_BITS"])
     if "BREAKFAST_B200_MERGE_CAPACITY" in os.environ:   # entries per rank of the multi-GPU label exchange (tests)
         opts["merge_capacity"] = int(os.environ["BREAKFAST_B200_MERGE_CAPACITY"])
+    if "BREAKFAST_B200_SHARD_PACK_FROM" in os.environ:   # rank count from which the sketch pass is sharded (default: never on one box)
+        opts["shard_pack_from"] = int(os.environ["BREAKFAST_B200_SHARD_PACK_FROM"])
     return opts
 
 

@@ -364,10 +364,12 @@ def test_single_process_multi_device_engine(monkeypatch, tmp_path):
     helpers.assert_matches(case, case["expected"], (tmp_path / "clusters.tsv").read_text())
 
 
+@pytest.mark.parametrize("shard_pack", [False, True], ids=["replicated-sketch-pass", "sharded-sketch-pass"])
 @pytest.mark.parametrize("merge_capacity", [0, 64], ids=["auto", "tiny-exchange-buffer"])
-def test_in_library_communicator_on_distinct_devices(merge_capacity, monkeypatch):
+def test_in_library_communicator_on_distinct_devices(merge_capacity, shard_pack, monkeypatch):
     """two (or four) real GPUs in one process: bf_comm_init_all gives the contexts the library's NCCL communicator, the
-    sketch pass is sharded and the union-finds are exchanged inside bf_run; labels and edges equal the single-GPU answer,
+    union-finds are exchanged inside bf_run and - with shard_pack_from = 2 - the sketch pass is sharded and its shares
+    all-gathered (the default replicates it on one box: measured faster); labels and edges equal the single-GPU answer,
     for the full run and for the incremental rectangle, with a deliberately small exchange capacity (overflow -> rerun)"""
     from breakfast_b200 import engine
     n_dev = _native.device_count()
@@ -376,6 +378,8 @@ def test_in_library_communicator_on_distinct_devices(merge_capacity, monkeypatch
     devices = list(range(4 if n_dev >= 4 else 2))
     if merge_capacity:
         monkeypatch.setenv("BREAKFAST_B200_MERGE_CAPACITY", str(merge_capacity))
+    if shard_pack:
+        monkeypatch.setenv("BREAKFAST_B200_SHARD_PACK_FROM", "2")
     indptr, indices, n_cols = synth.generate(30000, seed=17).csr()
     want_labels, _ = oracle.cluster(indptr, indices, 2)
     ws, wd = oracle.edges(indptr, indices, 2)
