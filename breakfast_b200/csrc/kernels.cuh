@@ -1,22 +1,24 @@
 // kernels.cuh — sm_100a device code for the breakfast distance-and-clustering hot path.
 //
-// Pipeline (one pass = bf_run), default form (128/256-bit sketches, tensor-core level 1):
-//   K1a k_pack_sketch_rows                                       CSR in storage order -> staged sketches + sort keys
+// Pipeline (one pass = bf_run), default form (128/256-bit sketches, tensor-core level 1), nine launches:
+//   K1a k_pack_sketch_rows16 (k_pack_sketch_rows on the plain CSR)  matrix in storage order -> staged sketches + sort keys
 //                                                               (replaces csr_matrix + row sums, breakfast.py:214,287)
-//   K2  4x(k_sort_hist, k_sort_scan_digits, k_sort_scatter)      rows sorted by (cardinality, cardinality on one hash half)
+//   K2  k_radix_sort (one cooperative kernel, all passes)        rows sorted by (cardinality, two hash-half cardinalities)
 //                                                               (replaces the np.isclose band, breakfast.py:250-254)
 //   K1b k_permute_store                                          staged sketches -> tile-blocked bitsets, fold planes,
-//                                                               +-1 int8 operands
-//   K2b k_schedule (+ scan of the item counts by its last block) + k_expand_items   three-key band-pruned work list
-//   K3a k_pairs_l1_imma                                          level 1: int8 mma.sync on the 32-bit folds, survivors queued
+//                                                               int8 operands of level 1; union-find init
+//   K2b k_schedule (its last block scans the item counts) + k_expand_items   three-key band-pruned tile-pair work list
+//   K3a k_pairs_l1_imma2                                         level 1: int8 mma.sync on the 32-bit folds, two column rows
+//                                                               per accumulator, dynamic item scheduler, survivors queued
 //   K3b k_pairs_l2_unit                                          level 2: exact 32-bit test, full-width XOR/POPC, candidates
 //                                                               (K3a+K3b replace sklearn _sparse_manhattan + _reduce_func,
 //                                                                sklearn/metrics/_pairwise_fast.pyx:76-107, breakfast.py:226-228)
 //   K3c k_verify_unite                                           exact |A xor B| on CSR rows of the candidates + union
-//   K4  k_uf_* (hook / path halving / labels)                    replaces _to_graph + networkx connected_components
+//   K4  k_uf_labels (hook / path halving inside K3c)             replaces _to_graph + networkx connected_components
 //                                                               (breakfast.py:93-113,325-326)
 // Other forms: k_card_keys + k_pack_sketch / k_pack_full (wider sketches, FULL engine), k_pairs<K4> (single-kernel
-// tiled XOR/POPC + threshold + compaction), k_pairs_l1 + k_pairs_l2 (level 1 on the integer pipes).
+// tiled XOR/POPC + threshold + compaction), k_pairs_l1_imma (one column row per accumulator), k_pairs_l1 + k_pairs_l2
+// (level 1 on the integer pipes), k_hj_* (hash-join engine).
 //
 // Bitset layout in HBM ("tile-blocked"): rows are in sort-key order (K2), grouped in tiles of
 // TILE=128 rows.  A row's bitset is cut into chunks of 4*K4 32-bit words (K4 = 16-byte groups per
