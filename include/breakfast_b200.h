@@ -112,7 +112,10 @@ void bf_ctx_destroy(bf_ctx* ctx);
  * single-chunk sketches; exact either way), "level1" (0 = level 1 on the integer
  * pipes, 1 = on the tensor cores: int8 mma.sync on +-1 expanded folds, 2 (default) = the same with two
  * column rows per accumulator; 128/256-bit sketches), "l1_ctas" (CTAs per SM of the level-1 kernel of
- * "level1" = 2: 1 or 2, 0 = default), "items_capacity" / "units_capacity" (entries of the expanded work list and
+ * "level1" = 2: 1 or 2, 0 = default), "l2_sub" (CTAs of the level-2 kernel per queue segment, 0 = default),
+ * "resident_csr16" (default 1: bf_upload_csr also keeps the compact 16-bit form of the matrix on the device and the
+ * sketch pass streams it), "verify_csr16" (default 0: 1 = the verification reads that form too; measured slower),
+ * "shard_pack_from" (rank count from which a multi-GPU pass shards its sketch pass; default 16 = replicated on one box), "items_capacity" / "units_capacity" (entries of the expanded work list and
  * of the level-2 queue, 0 = automatic), "merge_capacity" (entries per rank of the compact label exchange of a
  * multi-GPU pass, 0 = automatic). */
 int bf_ctx_set_option(bf_ctx* ctx, const char* key, int64_t value);
