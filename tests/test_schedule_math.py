@@ -86,3 +86,43 @@ def test_packed_pair_threshold_arithmetic_of_the_tensor_core_level1():
             byte = 0x41 ^ (0x7E if a else 0) ^ (0x80 if b else 0)
             val = byte - 256 if byte >= 128 else byte
             assert val == (-1 if a else 1) + 64 * (-1 if b else 1)
+
+
+def test_packed_level1_end_to_end_on_random_folds():
+    """The whole level-1 chain of k_pairs_l1_imma2 on the CPU: 32-bit folds -> +-1 int8 row operand, packed int8 column
+    operand (expand_pm1_pair: two rows per int8 row), int8 dot products as the MMA computes them (s32 accumulation),
+    one multiply + the two signed 16-bit halves, thresholds.  Survivor <=> popc(fa ^ fb) <= max_dist for either of the
+    two packed column rows (plus the complement alias, which only adds survivors)."""
+    rng = np.random.default_rng(11)
+    n_rows, n_cols = 96, 64
+    fa = rng.integers(0, 2 ** 32, size=n_rows, dtype=np.uint64).astype(np.uint32)
+    fb = rng.integers(0, 2 ** 32, size=n_cols, dtype=np.uint64).astype(np.uint32)
+    # plant close pairs, identical folds and a complement
+    fb[0] = fa[0]
+    fb[1] = fa[1] ^ np.uint32(1 << 7)
+    fb[2] = fa[2] ^ np.uint32((1 << 3) | (1 << 30))
+    fb[3] = ~fa[3]
+    fb[5] = fa[4] ^ np.uint32(1 << 31)
+
+    def pm1(f):   # bit k set -> -1, clear -> +1
+        bits = (f[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        return (1 - 2 * bits.astype(np.int32)).astype(np.int8)
+
+    ea, eb = pm1(fa), pm1(fb)
+    packed = (eb[0::2].astype(np.int32) + 64 * eb[1::2].astype(np.int32))
+    assert packed.min() >= -128 and packed.max() <= 127
+    packed = packed.astype(np.int8)
+    acc = ea.astype(np.int32) @ packed.astype(np.int32).T            # [rows, packed columns], as the s32 accumulators
+    popc = np.array([[bin(int(a) ^ int(b)).count("1") for b in fb] for a in fa])
+    d = 32 - 2 * popc
+    assert np.array_equal(acc, d[:, 0::2] + 64 * d[:, 1::2])
+    w = (acc.astype(np.int64) * 66560 + 63 * 66560)
+    hi = w >> 16
+    lo = ((w & 0xFFFF) ^ 0x8000) - 0x8000
+    for max_dist in (0, 1, 2, 3, 5, 8, 15, 16, 31):
+        thr = 32 - 2 * max_dist
+        got = (hi >= 65 * thr + 31) | (lo >= 1024 * (thr - 1))
+        want = (popc[:, 0::2] <= max_dist) | (popc[:, 1::2] <= max_dist)
+        assert not (want & ~got).any()
+        extra = got & ~want
+        assert (popc[:, 0::2][extra] == 32).all()
