@@ -92,7 +92,36 @@ def write_output(meta_nodups, meta_original, outdir):
         raise RuntimeError("Output row count differs from input row count")
 
     outdir.mkdir(parents=True, exist_ok=True)
-    expanded[["id", "cluster_id"]].to_csv(outdir / "clusters.tsv", sep="\t", index=False)
+    if not _write_clusters_arrow(expanded["id"], renumbered, clustered, outdir / "clusters.tsv"):
+        expanded[["id", "cluster_id"]].to_csv(outdir / "clusters.tsv", sep="\t", index=False)
+
+
+def _write_clusters_arrow(ids, renumbered, clustered, path) -> bool:
+    """clusters.tsv through pyarrow's CSV writer - the bytes pandas' to_csv(sep="\\t", index=False) writes (reference
+    breakfast.py:64-69), several times faster at 10^6 rows.  Only for the plain case: string ids without missing values
+    and without a character that the csv module would quote (tab, double quote, line break); anything else returns False
+    and the caller takes the pandas path, which is the reference's own."""
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        import pyarrow.csv as pcsv
+        arr = pa.array(ids)
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        if not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)) or arr.null_count:
+            return False
+        if pc.any(pc.match_substring_regex(arr, '["\t\n\r]')).as_py():
+            return False
+        values = np.zeros(len(renumbered), dtype=np.int64)
+        values[clustered] = renumbered[clustered].astype(np.int64)
+        col = pa.array(values, mask=~clustered)
+        table = pa.table({"id": arr, "cluster_id": col})
+        with open(path, "wb") as fh:
+            fh.write(b"id\tcluster_id\n")
+            pcsv.write_csv(table, fh, pcsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+        return True
+    except Exception:   # any surprise in the fast writer: the pandas path decides
+        return False
 
 
 # --------------------------------------------------------------------------------------------

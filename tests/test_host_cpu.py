@@ -127,6 +127,27 @@ def test_write_output_renumbers_by_first_appearance(tmp_path):
 
 
 # ------------------------------------------------------------------ cache re-indexing
+@pytest.mark.parametrize("ids", [
+    ["s1", "s2", "s3", "s4", "s5", "s6"],                    # plain: the pyarrow writer
+    ["a b", "é", "", "x,y", "007", "s'6"],                   # still plain for the csv module
+    ["s\t1", "s2", "s3", "s4", "s5", "s6"],                  # a tab: quoted by the csv module -> pandas path
+    ['s"1', "s2", "s3", "s4", "s5", "s6"],                   # a quote
+    ["s\n1", "s2", "s3", "s4", "s5", "s6"],                  # a line break
+    [11, 12, 13, 14, 15, 16],                                # numeric ids
+], ids=["plain", "odd-but-plain", "tab", "quote", "newline", "numeric"])
+@pytest.mark.parametrize("labels", [[3, 3, None, 7, 7, 3], [None] * 6, [5, 4, 3, 2, 1, 5]], ids=["mixed", "none", "all"])
+def test_fast_clusters_writer_is_byte_identical_to_pandas(ids, labels, tmp_path, monkeypatch):
+    """write_output's pyarrow writer against the pandas writer the reference uses (breakfast.py:64-69): same bytes for
+    plain ids, and it steps aside (returns False) for anything the csv module would quote or that is not a string"""
+    original = pd.DataFrame({"id": ids, "feature": ["f"] * 6})
+    nodups = pd.DataFrame({"id": [(i,) for i in ids], "feature": ["f"] * 6,
+                           "cluster_id": pd.Series([pd.NA if v is None else v for v in labels], dtype=object)})
+    breakfast.write_output(nodups, original, tmp_path / "fast")
+    monkeypatch.setattr(breakfast, "_write_clusters_arrow", lambda *a, **k: False)
+    breakfast.write_output(nodups, original, tmp_path / "pandas")
+    assert (tmp_path / "fast" / "clusters.tsv").read_bytes() == (tmp_path / "pandas" / "clusters.tsv").read_bytes()
+
+
 def test_cache_map_and_update_with_ghost_list():
     cached = pd.Series(["A", "A g", "A g h", "Q"])
     new = pd.Series(["A g h", "N", "A"])                    # "A g" and "Q" vanished, "N" is new
