@@ -462,7 +462,16 @@ int64_t bfh_string_bytes(void* h) { return (int64_t)static_cast<State*>(h)->s_by
 void bfh_get_results(void* h, int32_t* codes, int32_t* first_seq, int32_t* invalid, int64_t* u_ptr, int32_t* u_idx,
                      int64_t* b_ptr, int32_t* b_idx, int64_t* s_off, char* s_bytes) {
     State* st = static_cast<State*>(h);
-    auto cp = [](void* dst, const void* src, size_t bytes) { if (dst && bytes) memcpy(dst, src, bytes); };
+    // the big arrays (token and column indices, profile strings: hundreds of MB at 10^6 profiles) are copied by all
+    // host threads, each a contiguous slice
+    const int T = std::max(1, st->n_threads);
+    auto cp = [T](void* dst, const void* src, size_t bytes) {
+        if (!dst || !bytes) return;
+        if (bytes < ((size_t)8 << 20) || T == 1) { memcpy(dst, src, bytes); return; }
+        parallel_ranges((int64_t)bytes, T, [=](int, int64_t lo, int64_t hi) {
+            memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, (size_t)(hi - lo));
+        });
+    };
     cp(codes, st->codes.data(), st->codes.size() * 4);
     cp(first_seq, st->first_seq.data(), st->first_seq.size() * 4);
     cp(invalid, st->invalid.data(), st->invalid.size() * 4);
