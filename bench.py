@@ -119,8 +119,34 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
+        self.nvml_rows, self.nvml_stop, self.nvml_thread = [], threading.Event(), None
+
+    def _nvml_loop(self):
+        """NVML polled every 2 ms next to nvidia-smi: a timed region of a few milliseconds still holds several samples.
+        Any NVML trouble just ends this loop - the nvidia-smi rows remain."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.nvml_stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.nvml_rows.append((time.time(), int(sm), int(mx), int(mask)))
+                time.sleep(0.002)
+            pynvml.nvmlShutdown()
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -146,6 +172,18 @@ class ClockSampler:
         time.sleep(0.06)
         self.proc.terminate()
         self.thread.join(timeout=2)
+        self.nvml_stop.set()
+        if self.nvml_thread is not None:
+            self.nvml_thread.join(timeout=2)
+        fine = [r for r in self.nvml_rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        if len(fine) >= 3:
+            # bits of nvmlClocksEventReasons: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            sm = sorted(r[1] for r in fine)
+            reasons = sorted({name for r in fine for bit, name in bits.items() if r[3] & bit})
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in fine), "reasons": reasons, "samples": len(sm),
+                    "scope": "timed region", "source": "NVML polled every 2 ms (nvidia-smi -lms 50 beside it: "
+                                                       f"{len(self.rows)} rows over warm-up + timed region)"}
         inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.05]
         scope = "timed region"
         if not inside:
