@@ -242,6 +242,74 @@ void bfh_get_distinct(void* h, char* bytes, int64_t* offsets) {
     offsets[n] = (int64_t)st->tokens.arena.size();
 }
 
+// ---- native verdicts for the two DNA notations (reference breakfast.py:135-184, the regular expressions restated as
+// byte scanners; classification order substitution, insertion, deletion; trimming applies to substitutions only and
+// is inclusive at both ends).  Only pure-ASCII tokens without a line break are judged here - for those Python's
+// `re` (\d, [A-Z], ., $) and these scanners agree by construction; every other token gets BFH_ASK_PYTHON and the
+// caller runs the reference's own expressions on it.
+enum { BFH_KEEP = 0, BFH_DROP = 1, BFH_INVALID = 2, BFH_ASK_PYTHON = 255 };
+namespace {
+inline bool is_up(char c) { return c >= 'A' && c <= 'Z'; }
+inline bool is_dig(char c) { return c >= '0' && c <= '9'; }
+// ^[A-Z](\d+)[A-Z]$ -> position (saturated) in *pos
+inline bool match_substitution(const char* p, size_t n, int64_t* pos) {
+    if (n < 3 || !is_up(p[0]) || !is_up(p[n - 1])) return false;
+    int64_t v = 0;
+    for (size_t i = 1; i + 1 < n; ++i) {
+        if (!is_dig(p[i])) return false;
+        v = v > (INT64_MAX - 9) / 10 ? INT64_MAX : v * 10 + (p[i] - '0');
+    }
+    *pos = v;
+    return true;
+}
+// \d+ starting at i; returns the index after the digits (i itself if there is none)
+inline size_t skip_digits(const char* p, size_t n, size_t i) { while (i < n && is_dig(p[i])) ++i; return i; }
+inline bool match_insertion(int type, const char* p, size_t n) {
+    if (type == 0) return n >= 2 && is_up(p[n - 1]) && is_up(p[n - 2]);          // covsonar_dna  ^.*[A-Z][A-Z]$
+    size_t i = skip_digits(p, n, 0);                                               // nextclade_dna ^\d+:[A-Z]+$
+    if (i == 0 || i >= n || p[i] != ':' || i + 1 >= n) return false;
+    for (size_t k = i + 1; k < n; ++k) if (!is_up(p[k])) return false;
+    return true;
+}
+inline bool match_deletion(int type, const char* p, size_t n) {
+    if (type == 0) {                                                               // covsonar_dna  ^del:\d+:\d+$
+        if (n < 7 || memcmp(p, "del:", 4) != 0) return false;
+        size_t i = skip_digits(p, n, 4);
+        if (i == 4 || i >= n || p[i] != ':') return false;
+        const size_t j = skip_digits(p, n, i + 1);
+        return j > i + 1 && j == n;
+    }
+    size_t i = skip_digits(p, n, 0);                                               // nextclade_dna ^\d+(-\d+)?$
+    if (i == 0) return false;
+    if (i == n) return true;
+    if (p[i] != '-') return false;
+    const size_t j = skip_digits(p, n, i + 1);
+    return j > i + 1 && j == n;
+}
+}  // namespace
+
+// var_type: 0 = covsonar_dna, 1 = nextclade_dna.  upper_cut = reference_length - trim_end.  verdict[n_distinct] out.
+// Returns the number of tokens left to Python (BFH_ASK_PYTHON).
+int32_t bfh_classify_dna(void* h, int32_t var_type, int32_t skip_ins, int32_t skip_del, int64_t trim_start, int64_t upper_cut,
+                         uint8_t* verdict) {
+    State* st = static_cast<State*>(h);
+    const int32_t n = (int32_t)st->tokens.off.size();
+    int32_t ask = 0;
+    for (int32_t t = 0; t < n; ++t) {
+        const char* p = st->tokens.arena.data() + st->tokens.off[t];
+        const size_t len = (size_t)st->tokens.len[t];
+        bool plain = true;
+        for (size_t i = 0; i < len; ++i) plain &= ((unsigned char)p[i] < 0x80) && p[i] != '\n';
+        if (!plain) { verdict[t] = BFH_ASK_PYTHON; ++ask; continue; }
+        int64_t pos = 0;
+        if (match_substitution(p, len, &pos)) verdict[t] = (pos <= trim_start || pos >= upper_cut) ? BFH_DROP : BFH_KEEP;
+        else if (match_insertion(var_type, p, len)) verdict[t] = skip_ins ? BFH_DROP : BFH_KEEP;
+        else if (match_deletion(var_type, p, len)) verdict[t] = skip_del ? BFH_DROP : BFH_KEEP;
+        else verdict[t] = BFH_INVALID;
+    }
+    return ask;
+}
+
 // verdict[distinct token]: 0 keep, 1 drop silently, 2 invalid (dropped and reported).
 // filter_active = 0: profiles are compared (and returned) as raw strings, tokens are only needed for the
 // matrix; empty tokens never enter the matrix (breakfast.py:208-209).

@@ -37,6 +37,8 @@ def _load():
             getattr(lib, name).restype = i32
             getattr(lib, name).argtypes = [vp]
         lib.bfh_get_distinct.argtypes = [vp, vp, vp]
+        lib.bfh_classify_dna.restype = i32
+        lib.bfh_classify_dna.argtypes = [vp, i32, i32, i32, i64, i64, vp]
         lib.bfh_build.argtypes = [vp, vp, C.c_int]
         lib.bfh_get_results.argtypes = [vp] + [vp] * 9
         lib.bfh_free.argtypes = [vp]
@@ -62,6 +64,14 @@ def available() -> bool:
         return False
     _load()   # OSError / AttributeError propagate: the .so exists but is unusable
     return True
+
+
+_NATIVE_TYPES = {"covsonar_dna": 0, "nextclade_dna": 1}   # --var-type values bfh_classify_dna knows
+_ASK_PYTHON = 255
+
+
+def _fits_i64(v) -> bool:
+    return -(2 ** 63) <= int(v) < 2 ** 63
 
 
 def host_threads() -> int:
@@ -118,13 +128,25 @@ def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, tri
         tok_off = np.empty(nd + 1, dtype=np.int64)
         lib.bfh_get_distinct(state, tok_bytes, tok_off.ctypes.data)
         raw = tok_bytes.raw
-        tokens = [raw[tok_off[i]:tok_off[i + 1]].decode("utf-8") for i in range(nd)]
+
+        def token(i):
+            return raw[tok_off[i]:tok_off[i + 1]].decode("utf-8")
 
         filter_active = bool(skip_del or skip_ins or trim_start > 0 or trim_end > 0)
         verdict = np.zeros(max(nd, 1), dtype=np.uint8)
         if filter_active and feature_type != "raw":
             classify = _token_classifier(feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length)
-            verdict[:nd] = [classify(t) for t in tokens]
+            upper_cut = reference_length - trim_end
+            if feature_type in _NATIVE_TYPES and _fits_i64(trim_start) and _fits_i64(upper_cut):
+                # the two DNA notations are judged natively (byte scanners that restate the reference's expressions for
+                # ASCII tokens); whatever is not plain ASCII comes back as _ASK_PYTHON and gets the expressions themselves
+                left = lib.bfh_classify_dna(state, _NATIVE_TYPES[feature_type], int(bool(skip_ins)), int(bool(skip_del)),
+                                            int(trim_start), int(upper_cut), verdict.ctypes.data)
+                if left:
+                    for i in np.flatnonzero(verdict[:nd] == _ASK_PYTHON).tolist():
+                        verdict[i] = classify(token(i))
+            else:
+                verdict[:nd] = [classify(token(i)) for i in range(nd)]
         lib.bfh_build(state, verdict.ctypes.data, int(filter_active))
 
         n_unique = lib.bfh_n_unique(state)
@@ -147,7 +169,7 @@ def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, tri
     if filter_active and feature_type != "raw":
         assert _INVALID == 2
         for t in invalid.tolist():
-            print(f"Skipping invalid feature: '{tokens[t]}'")
+            print(f"Skipping invalid feature: '{token(t)}'")
     print(f"Number of duplicates: {n_seq - n_unique}")
     # ids of every unique profile as a tuple, in first-appearance order of the profiles
     ids = meta["id"].to_numpy(dtype=object)

@@ -287,6 +287,41 @@ def test_native_host_path_nextclade_and_multichar_separator(capsys):
     assert [fwd[x] for x in pre["token_indices"].tolist()] == indices.tolist()
 
 
+@pytest.mark.parametrize("var_type", ["covsonar_dna", "nextclade_dna"])
+@pytest.mark.parametrize("flags", [(True, True, 264, 228), (False, True, 0, 0), (True, False, 5, 29000), (False, False, 1, 0)],
+                         ids=lambda f: "-".join(map(str, f)))
+def test_native_token_verdicts_equal_the_reference_expressions(var_type, flags, capsys):
+    """bfh_classify_dna (byte scanners) against the reference's regular expressions (breakfast.py:135-184) on tokens
+    built to sit on every edge of the patterns - short forms, missing parts, lower case, huge positions, trim
+    boundaries, non-ASCII digits and letters, line breaks - plus random strings over the patterns' alphabet"""
+    from breakfast_b200 import hostfast
+    skip_ins, skip_del, trim_start, trim_end = flags
+    reflen = 29903
+    rng = np.random.default_rng(5)
+    edge = ["A1T", "A12T", "AT", "A", "", "1", "A1", "1A", "a1T", "A1t", "A1TT", "AA1T", "A 1T", "A1.T", "A-1T", "A+1T",
+            "A0T", "A00012T", "A264T", "A265T", "A29674T", "A29675T", "A29676T", "A5T", "A6T", "A28999T", "A29000T",
+            "A99999999999999999999999999T", "A9223372036854775807T", "A9223372036854775808T",
+            "AB", "xAB", "12AB", "A1AB", "ab", "aB", "Ab", "ABc", ":AB", "del:1:1", "del:1:", "del::1", "del:1", "del:1:1:1",
+            "del:12:34", "Del:1:1", "del:1:1A", "del:1:1AB", "del:a:1", "del:1:b", "del: 1:1", "12:A", "12:ACGT", "12:", ":A",
+            "12:a", "12:A1", "1:AB", "12", "12-13", "12-", "-12", "12--13", "12-13-14", "0", "007", "1-2A", "12:AC GT",
+            "A1T\n", "AB\n", "del:1:1\n", "12\n", "\nA1T", "A１２T", "A1Ｔ", "ÉB", "AÉ", "A٣T", "12٣", "del:١:1", "é1"]
+    alphabet = list("ACGTNdel:-0123456789 aX.") + ["É", "٣"]
+    fuzz = ["".join(rng.choice(alphabet, size=int(rng.integers(0, 9)))) for _ in range(4000)]
+    tokens = sorted(set(edge + fuzz) - {""}) + [""]
+    tokens = [t for t in tokens if "|" not in t]
+    # one profile per token (plus one with all of them), separator "|"
+    meta = pd.DataFrame({"id": [f"s{i}" for i in range(len(tokens) + 1)], "feature": tokens + ["|".join(tokens)]})
+    opts = (var_type, skip_ins, skip_del, trim_start, trim_end, reflen)
+    capsys.readouterr()
+    nd_py, indptr, indices, n_vocab = _python_path(meta, "|", opts)
+    out_py = capsys.readouterr().out
+    nd_c, pre = hostfast.prepare(meta, "|", *opts)
+    out_c = capsys.readouterr().out
+    assert out_c == out_py
+    assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
+    assert pre["n_vocab"] == n_vocab and np.array_equal(pre["token_indptr"], indptr)
+
+
 # ------------------------------------------------------------------ no CPU fallback, no oracle in the product
 def test_product_never_imports_the_oracle():
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|ref_port|liboracle", re.M)
