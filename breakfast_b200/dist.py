@@ -69,7 +69,10 @@ class RankRunner:
         self.ctx.run(max_dist, self.rank, self.world)
         if self.world > 1 and getattr(self.ctx, "comm", None) is None:
             self.ctx.labels_to_device(self.local.data_ptr())
-            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)   # device tensors: NCCL
+            if self.local.is_cuda:
+                dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+            else:   # gloo (CPU tests of the host logic)
+                dist.all_gather(list(self.gathered.unbind(0)), self.local, group=self.group)
             self.ctx.merge_labels_device(self.gathered.data_ptr(), self.world)
 
     def run_sync(self, max_dist: int, attempts: int = 6):
