@@ -71,7 +71,7 @@ class RankRunner:
             self.ctx.labels_to_device(self.local.data_ptr())
             if self.local.is_cuda:
                 dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-            else:   # gloo (CPU tests of the host logic)
+            else:   # CPU tensors over gloo: tests/test_dist_gloo.py drives this class with a stand-in context
                 dist.all_gather(list(self.gathered.unbind(0)), self.local, group=self.group)
             self.ctx.merge_labels_device(self.gathered.data_ptr(), self.world)
 
