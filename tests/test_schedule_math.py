@@ -126,3 +126,24 @@ def test_packed_level1_end_to_end_on_random_folds():
         assert not (want & ~got).any()
         extra = got & ~want
         assert (popc[:, 0::2][extra] == 32).all()
+
+
+def test_compact_form_hash_identities_of_the_sketch_pass():
+    """k_pack_sketch_rows16 never rebuilds a 17-bit column: it hashes the low 16 bits and adds C << 16 for the columns
+    from 65536 on (the multiplicative hash distributes), takes the sketch bit from the top log2(m) bits and the two
+    sort-key halves from hash bits 31 and 30.  CPU restatement against the plain-column formulas of k_pack_sketch_rows
+    (fold_hash) and tools/schedule_sim.row_keys."""
+    C = 2654435761
+    cols = np.concatenate([np.arange(0, 131072, 7), [0, 1, 65535, 65536, 65537, 131071]]).astype(np.uint64)
+    h_plain = (cols * C) & 0xFFFFFFFF
+    lo, hi = cols & 0xFFFF, cols >> 16
+    h_compact = (lo * C + hi * ((C << 16) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    assert np.array_equal(h_plain, h_compact)
+    for log2m in (7, 8):
+        bit_plain = h_plain >> (32 - log2m)                       # fold_hash
+        word, bit = h_compact >> (37 - log2m), (h_compact >> (32 - log2m)) & 31
+        assert np.array_equal(bit_plain, word * 32 + bit)
+    # quadrant counters of a row: quad += h >> 30 and in_h1 += h >> 31  ->  s = |row n H1|, t = |row n H2|
+    quad, in_h1 = int((h_plain >> 30).sum()), int((h_plain >> 31).sum())
+    s, t = int(((h_plain >> 31) & 1).sum()), int(((h_plain >> 30) & 1).sum())
+    assert (in_h1, quad - 2 * in_h1) == (s, t)
