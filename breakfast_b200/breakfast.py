@@ -66,34 +66,36 @@ def write_output(meta_nodups, meta_original, outdir):
     """One line per input sequence, input order, clusters renumbered 1..K by first appearance,
     unclustered sequences get an empty field; written to <outdir>/clusters.tsv."""
     id_groups = meta_nodups["id"].tolist()
-    group_sizes = np.fromiter((len(g) for g in id_groups), dtype=np.int64, count=len(id_groups))
+    group_sizes = np.fromiter(map(len, id_groups), dtype=np.int64, count=len(id_groups))
     per_profile = np.empty(len(id_groups), dtype=object)
     per_profile[:] = meta_nodups["cluster_id"].tolist()
-    expanded = pd.DataFrame(
-        {
-            "id": list(chain.from_iterable(id_groups)),
-            "cluster_id": np.repeat(per_profile, group_sizes),
-        }
-    )
-    # back to the order of the input file
-    expanded = expanded.set_index("id").reindex(index=meta_original["id"]).reset_index()
+    flat_ids = list(chain.from_iterable(id_groups))
+    per_sequence = np.repeat(per_profile, group_sizes)
+    original_ids = meta_original["id"]
+    # back to the order of the input file.  Without repeated profiles the groups are already in that order (first
+    # appearance): then the input's own id column is written and the join on the ids is skipped.
+    if flat_ids == original_ids.tolist():
+        ids_out, raw, expanded = original_ids, per_sequence, None
+    else:
+        expanded = pd.DataFrame({"id": flat_ids, "cluster_id": per_sequence})
+        expanded = expanded.set_index("id").reindex(index=original_ids).reset_index()
+        ids_out, raw = expanded["id"], expanded["cluster_id"].to_numpy(dtype=object)
 
     # engine labels -> 1..K in order of first appearance in the input
-    raw = expanded["cluster_id"].to_numpy(dtype=object)
     clustered = ~pd.isna(raw)
     renumbered = np.empty(raw.size, dtype=object)
     renumbered[:] = pd.NA
     if clustered.any():
         codes, _ = pd.factorize(raw[clustered], sort=False)
         renumbered[clustered] = (codes + 1).tolist()
-    expanded["cluster_id"] = renumbered
 
-    if expanded.shape[0] != meta_original.shape[0]:
+    if raw.size != meta_original.shape[0]:
         raise RuntimeError("Output row count differs from input row count")
 
     outdir.mkdir(parents=True, exist_ok=True)
-    if not _write_clusters_arrow(expanded["id"], renumbered, clustered, outdir / "clusters.tsv"):
-        expanded[["id", "cluster_id"]].to_csv(outdir / "clusters.tsv", sep="\t", index=False)
+    if not _write_clusters_arrow(ids_out, renumbered, clustered, outdir / "clusters.tsv"):
+        frame = pd.DataFrame({"id": ids_out.to_numpy() if expanded is None else expanded["id"], "cluster_id": renumbered})
+        frame[["id", "cluster_id"]].to_csv(outdir / "clusters.tsv", sep="\t", index=False)
 
 
 def _write_clusters_arrow(ids, renumbered, clustered, path) -> bool:
