@@ -29,6 +29,8 @@ def _load():
         lib.bfh_tokenise.argtypes = [C.c_char_p, i64, C.c_char, C.c_char_p, i32, i64]
         lib.bfh_tokenise_arrow.restype = vp
         lib.bfh_tokenise_arrow.argtypes = [vp, vp, i32, i64, C.c_char_p, i32, i32]
+        lib.bfh_tokenise_arrow_chunks.restype = vp
+        lib.bfh_tokenise_arrow_chunks.argtypes = [i32, vp, vp, vp, i32, C.c_char_p, i32, i32]
         for name in ("bfh_n_tokens", "bfh_distinct_bytes", "bfh_n_unique", "bfh_n_invalid", "bfh_token_nnz",
                      "bfh_binary_nnz", "bfh_string_bytes"):
             getattr(lib, name).restype = i64
@@ -83,20 +85,30 @@ def host_threads() -> int:
 
 
 def _arrow_strings(series):
-    """(arrow array, data pointer, offsets pointer, offset width) of a pandas string column, or None when the column
-    holds missing values or cannot be viewed as one contiguous Arrow string array"""
+    """(arrow chunks, data pointers, offset pointers, rows per chunk, offset width) of a pandas string column - read in
+    place, chunk by chunk (the Arrow CSV reader hands over hundreds of chunks per million lines; gluing them together
+    would copy the whole column) - or None when the column holds missing values or is not an Arrow string column"""
     import pyarrow as pa
     try:
         arr = pa.array(series)
     except (pa.ArrowInvalid, pa.ArrowTypeError, TypeError):
         return None
-    if isinstance(arr, pa.ChunkedArray):
-        arr = arr.combine_chunks()
-    if arr.null_count or not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+    chunks = list(arr.chunks) if isinstance(arr, pa.ChunkedArray) else [arr]
+    if not chunks:
         return None
-    width = 8 if pa.types.is_large_string(arr.type) else 4
-    _, offsets, data = arr.buffers()
-    return arr, (data.address if data is not None else 0), offsets.address + arr.offset * width, width
+    kind = chunks[0].type
+    if not (pa.types.is_string(kind) or pa.types.is_large_string(kind)):
+        return None
+    width = 8 if pa.types.is_large_string(kind) else 4
+    data_ptrs, off_ptrs, rows = [], [], []
+    for ch in chunks:
+        if ch.null_count or ch.type != kind:
+            return None
+        _, offsets, data = ch.buffers()
+        data_ptrs.append(data.address if data is not None else 0)
+        off_ptrs.append(offsets.address + ch.offset * width)
+        rows.append(len(ch))
+    return chunks, data_ptrs, off_ptrs, rows, width
 
 
 def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, trim_end, reference_length, threads=None):
@@ -117,9 +129,11 @@ def prepare(meta, feature_sep, feature_type, skip_ins, skip_del, trim_start, tri
     view = _arrow_strings(meta["feature"])
     if view is None:
         return None
-    arr, data_ptr, off_ptr, width = view
+    arr, data_ptrs, off_ptrs, rows, width = view   # `arr` keeps the buffers alive until bfh_build is done with them
     lib = _load()
-    state = lib.bfh_tokenise_arrow(data_ptr, off_ptr, width, n_seq, sep_b, len(sep_b), int(threads or host_threads()))
+    n_chunks = len(rows)
+    state = lib.bfh_tokenise_arrow_chunks(n_chunks, (C.c_void_p * n_chunks)(*data_ptrs), (C.c_void_p * n_chunks)(*off_ptrs),
+                                          (C.c_int64 * n_chunks)(*rows), width, sep_b, len(sep_b), int(threads or host_threads()))
     if not state:
         return None
     try:

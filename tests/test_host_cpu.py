@@ -287,6 +287,39 @@ def test_native_host_path_nextclade_and_multichar_separator(capsys):
     assert [fwd[x] for x in pre["token_indices"].tolist()] == indices.tolist()
 
 
+@pytest.mark.parametrize("kind", ["large_string", "string"])
+def test_native_host_path_reads_a_chunked_arrow_column_in_place(kind, capsys):
+    """the profile column as the Arrow CSV reader leaves it: many chunks, one of them a slice with a non-zero offset, one
+    empty - tokenised in place (bfh_tokenise_arrow_chunks), same result as the Python path on the same strings"""
+    import pyarrow as pa
+    from breakfast_b200 import hostfast
+    meta = breakfast.read_input(GOLDEN / "synthetic/syn_dna.tsv.gz", "\t", "accession", "dna_profile")
+    profiles = meta["feature"].tolist()
+    typ = pa.large_string() if kind == "large_string" else pa.string()
+    cuts = [0, 1, 2, 50, 50, 333, len(profiles)]
+    chunks = [pa.array(profiles[a:b], type=typ) for a, b in zip(cuts[:-1], cuts[1:])]
+    padded = pa.array(["zzz"] * 7 + profiles[2:50] + ["yyy"], type=typ)
+    chunks[2] = padded.slice(7, 48)                       # a chunk whose offsets do not start at its buffer
+    column = pa.chunked_array(chunks, type=typ)
+    assert column.num_chunks == 6 and column.to_pylist() == profiles
+    chunked = pd.DataFrame({"id": meta["id"], "feature": pd.Series(pd.arrays.ArrowStringArray(column), dtype=meta["feature"].dtype)})
+    opts = ("covsonar_dna", True, True, 264, 228, 29903)
+    capsys.readouterr()
+    nd_py, indptr, indices, n_vocab = _python_path(meta, " ", opts)
+    out_py = capsys.readouterr().out
+    nd_c, pre = hostfast.prepare(chunked, " ", *opts)
+    out_c = capsys.readouterr().out
+    assert out_c == out_py
+    assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
+    assert pre["n_vocab"] == n_vocab and np.array_equal(pre["token_indptr"], indptr)
+    # and with no filter active (profiles compared and returned as raw strings)
+    raw_opts = ("covsonar_dna", False, False, 0, 0, 29903)
+    nd_py, indptr, _, n_vocab = _python_path(meta, " ", raw_opts)
+    nd_c, pre = hostfast.prepare(chunked, " ", *raw_opts)
+    assert nd_c["id"].tolist() == nd_py["id"].tolist() and nd_c["feature"].tolist() == nd_py["feature"].tolist()
+    assert pre["n_vocab"] == n_vocab and np.array_equal(pre["token_indptr"], indptr)
+
+
 @pytest.mark.parametrize("var_type", ["covsonar_dna", "nextclade_dna"])
 @pytest.mark.parametrize("flags", [(True, True, 264, 228), (False, True, 0, 0), (True, False, 5, 29000), (False, False, 1, 0)],
                          ids=lambda f: "-".join(map(str, f)))
