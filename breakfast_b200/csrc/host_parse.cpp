@@ -45,6 +45,28 @@ inline uint64_t hash_bytes(const char* p, size_t n) {
     return h;
 }
 
+// A big array that is written completely by the threads that fill it: plain malloc, no value-initialisation (a
+// std::vector would zero hundreds of MB on one thread first, and take the page faults there too)
+template <typename T>
+struct RawVec {
+    T* p = nullptr;
+    size_t n = 0;
+    RawVec() = default;
+    RawVec(const RawVec&) = delete;
+    RawVec& operator=(const RawVec&) = delete;
+    ~RawVec() { free(p); }
+    void resize(size_t m) {
+        free(p);
+        p = static_cast<T*>(malloc(std::max<size_t>(m, 1) * sizeof(T)));
+        n = p ? m : 0;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Interner {  // open addressing over (offset, length) into one byte arena
     std::vector<int32_t> slots;
     std::vector<int64_t> off;
@@ -89,12 +111,12 @@ struct State {
                                            // both relative to buf = the lowest of the buffers' addresses
     Interner tokens;
     std::vector<int64_t> tok_ptr;          // n_seq + 1
-    std::vector<int32_t> tok_ids;          // raw token occurrences (empty tokens included)
+    RawVec<int32_t> tok_ids;               // raw token occurrences (empty tokens included)
     // results of bfh_build
     std::vector<int32_t> codes, first_seq, invalid;
     std::vector<int64_t> u_ptr, b_ptr, s_off;
-    std::vector<int32_t> u_idx, b_idx;
-    std::string s_bytes;
+    RawVec<int32_t> u_idx, b_idx;
+    RawVec<char> s_bytes;
     int32_t n_vocab = 0, n_cols = 0;
 };
 
@@ -377,7 +399,7 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
     for (int32_t t = 0; t < n_distinct; ++t) is_empty[t] = st->tokens.len[t] == 0;
     st->codes.assign((size_t)n, -1);
     // ---- filter: kept token ids of all sequences, concatenated (every thread filters a contiguous range of records)
-    std::vector<int32_t> kept;
+    RawVec<int32_t> kept;
     std::vector<int64_t> kept_ptr((size_t)n + 1, 0);
     {
         struct Part { std::vector<int32_t> kept, invalid; int64_t lo = 0, hi = 0; };
@@ -508,7 +530,7 @@ int bfh_build(void* h, const uint8_t* verdict, int filter_active) {
         for (int64_t u = lo; u < hi; ++u) {
             const int64_t r = uniq_rows[(size_t)u];
             int32_t* out = st->u_idx.data() + st->u_ptr[(size_t)u];
-            char* sp = &st->s_bytes[0] + st->s_off[(size_t)u];
+            char* sp = st->s_bytes.data() + st->s_off[(size_t)u];
             for (int64_t k = kept_ptr[(size_t)r]; k < kept_ptr[(size_t)r + 1]; ++k) {
                 const int32_t t = kept[(size_t)k];
                 *out++ = vocab_of[(size_t)t];
