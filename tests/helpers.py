@@ -137,12 +137,23 @@ CONFIG4_OPTS = dict(max_dist=1, sep2=",", id_col="seqName", clust_col="substitut
 CONFIG5_OPTS = dict(max_dist=2, min_cluster_size=5)
 
 
+def frame_to_tsv(df) -> str:
+    """df.to_csv(sep="\\t", index=False) for a frame of plain strings - the same bytes, several times faster at 10^6 rows
+    (the csv module would only quote a field that holds a tab, a double quote or a line break: then pandas writes it)"""
+    cols = [df[c].tolist() for c in df.columns]
+    plain = all(isinstance(v, str) and not any(ch in v for ch in '\t"\n\r') for col in cols for v in col) and \
+        all(isinstance(c, str) and not any(ch in c for ch in '\t"\n\r') for c in df.columns)
+    if not plain or not cols or not cols[0]:
+        return df.to_csv(sep="\t", index=False)
+    return "\t".join(df.columns) + "\n" + "\n".join(map("\t".join, zip(*cols))) + "\n"
+
+
 def config4_table(n=500_000) -> str:
     """config 4: n unique nextclade_dna profiles with indels in the clustered column (several sequences per profile),
     to be run with --skip-ins --skip-del and wide trims (profiles collapse)"""
     from breakfast_b200 import synth
     prof = synth.generate(n, seed=4, with_mult=True, unique_on_all_events=True)
-    return prof.table("nextclade_dna", ",", id_col="seqName", feature_col="substitutions").to_csv(sep="\t", index=False)
+    return frame_to_tsv(prof.table("nextclade_dna", ",", id_col="seqName", feature_col="substitutions"))
 
 
 def _new_substitution(rng, profile_tokens):
@@ -197,4 +208,4 @@ def config5_tables(n=1_000_000, n_delta=50_000, seed=5):
     added = pd.DataFrame({"accession": [f"add{k:06d}" for k in range(n_add)], "dna_profile": new_feats})
     df1 = pd.concat([pd.DataFrame({"accession": ids[keep], "dna_profile": feats1[keep]}), added], ignore_index=True)
     df1 = df1.iloc[rng.permutation(len(df1))].reset_index(drop=True)
-    return df0.to_csv(sep="\t", index=False), df1.to_csv(sep="\t", index=False)
+    return frame_to_tsv(df0), frame_to_tsv(df1)
